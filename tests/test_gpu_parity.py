@@ -1,0 +1,564 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): allocated block sets bit-exact as sets; weights bit-exact;
+TSDF within 1e-5 absolute (bit-exact is asserted where the arithmetic is deterministic);
+ICP normal equations relative 1e-5; pose within 1e-4 in rotation and translation.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import entries_to_set, render, rot_err, small_cfg
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from voxelhashing_demo_b200 import POLICY_FIXED, POLICY_REF_EXACT, Config, Context, FramePipeline, scenes  # noqa: E402
+from voxelhashing_demo_b200 import lib as L  # noqa: E402
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def gpu_preprocess(ctx, depth):
+    d = cu(depth.reshape(-1))
+    v, n, df = ctx.new_maps()
+    ctx.preprocess(d, v, n, df)
+    torch.cuda.synchronize()
+    return v, n, df
+
+
+def fixed_cfg(**kw):
+    base = dict(policy=POLICY_FIXED, numBuckets=100003, numVoxelBlocks=8192, truncation=0.06, truncScale=0.01,
+                depthMin=0.1, depthMax=4.0, overflowSlots=4096)
+    base.update(kw)
+    return Config(**base)
+
+
+def compare_blocks(gpu_blocks: dict, cpu_blocks: dict, sdf_tol=1e-5):
+    assert set(gpu_blocks) == set(cpu_blocks)
+    worst = 0.0
+    exact = True
+    for k, g in gpu_blocks.items():
+        c = cpu_blocks[k]
+        assert np.array_equal(bits(g[:, 1]), bits(c[:, 1])), f"weights differ in block {k}"
+        d = float(np.max(np.abs(g[:, 0].astype(np.float64) - c[:, 0].astype(np.float64))))
+        worst = max(worst, d)
+        exact = exact and np.array_equal(bits(g[:, 0]), bits(c[:, 0]))
+    assert worst <= sdf_tol, f"max |sdf_gpu - sdf_oracle| = {worst}"
+    return exact, worst
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("policy", [POLICY_REF_EXACT, POLICY_FIXED])
+@pytest.mark.parametrize("size", ["vga", "small", "ragged"])
+def test_preprocess_bit_exact(built_library, oracle, policy, size):
+    if size == "vga":
+        cfg = Config(policy=policy)
+    elif size == "small":
+        cfg = small_cfg(policy=policy)
+    else:  # width/height not multiples of the 32x8 tile
+        cfg = small_cfg(policy=policy, width=161, height=123)
+    depth = render(cfg, scenes.scene_S1(), scenes.trajectory_C2(7))
+    depth[5:9, 10:40] = 0                 # holes
+    depth[0, 0] = 65535                   # out of sensor range in Fixed
+    ctx = Context(cfg)
+    v, n, df = gpu_preprocess(ctx, depth)
+    ov, on, odf = oracle.OracleTable(cfg).preprocess(depth)
+    assert np.array_equal(bits(v.cpu().numpy()), bits(ov))
+    assert np.array_equal(bits(n.cpu().numpy()), bits(on))
+    assert np.array_equal(bits(df.cpu().numpy()), bits(odf))
+
+
+def test_refexact_c1prime_exact(built_library, oracle):
+    """C1': reference defaults but 100003 buckets => no bucket contention => everything deterministic."""
+    cfg = Config(numBuckets=100003)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    pose = np.eye(4, dtype=np.float32)
+    ot = oracle.OracleTable(cfg)
+    ov, on, _ = ot.preprocess(depth)
+    rep, nvis, nupd = ot.fuse_frame(pose, ov)
+    assert rep.bucketsContended == 0 and rep.requestedBlocks == 234      # SURVEY.md Appendix B probe
+
+    ctx = Context(cfg)
+    v, n, _ = gpu_preprocess(ctx, depth)
+    ctx.fuse_frame(pose, v, n)
+    st = ctx.stats()
+    assert entries_to_set(ctx.export_entries()) == entries_to_set(ot.entries())
+    assert st.numVisible == nvis and st.numAllocated == rep.inserted and st.lastInserted == rep.inserted
+    assert entries_to_set(ctx.export_compact()) == entries_to_set(ot.compact_entries())
+    assert int(st.numUpdated) == nupd
+    exact, worst = compare_blocks(ctx.block_dict(), ot.block_dict())
+    assert exact, f"sdf not bit-exact (worst {worst})"
+    # second and third integration of the same frame: weights follow the same fp32 +0.1f chain
+    for _ in range(2):
+        ot.fuse_frame(pose, ov)
+        ctx.fuse_frame(pose, v, n)
+    exact, _ = compare_blocks(ctx.block_dict(), ot.block_dict())
+    assert exact
+
+
+def test_refexact_c1_contended_relaxed_rule(built_library, oracle):
+    """C1 as shipped (5000 buckets): 34 contended buckets; the reference is racy there (quirk Q4).
+    Relaxed rule of SURVEY.md section 8c."""
+    cfg = Config()
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    pose = np.eye(4, dtype=np.float32)
+    ot = oracle.OracleTable(cfg)
+    ov, _, _ = ot.preprocess(depth)
+    rep = ot.alloc(pose, ov)
+    assert rep.bucketsContended == 34 and rep.bucketsTouched == 199
+    requested_new = ot.last_requested_new()
+
+    ctx = Context(cfg)
+    v, n, _ = gpu_preprocess(ctx, depth)
+    ctx.set_pose(pose)
+    ctx.alloc_blocks(v, n)
+    got = entries_to_set(ctx.export_entries())
+    assert got <= requested_new                                   # allocated subset of requested
+    by_bucket_req, by_bucket_got = {}, {}
+    for k in requested_new:
+        by_bucket_req.setdefault(oracle.hash_block(cfg, *k), set()).add(k)
+    for k in got:
+        by_bucket_got.setdefault(oracle.hash_block(cfg, *k), set()).add(k)
+    for b, req in by_bucket_req.items():
+        assert len(by_bucket_got.get(b, ())) == 1                  # exactly one new block per touched bucket
+        if len(req) == 1:
+            assert by_bucket_got[b] == req                         # equality on un-contended buckets
+    assert ctx.stats().numAllocated == rep.inserted == 199
+    # repeating the frame max-multiplicity times converges to the full requested set
+    for _ in range(rep.maxNewPerBucket):
+        ot.alloc(pose, ov)
+        ctx.set_pose(pose)
+        ctx.alloc_blocks(v, n)
+    assert entries_to_set(ctx.export_entries()) == entries_to_set(ot.entries()) == requested_new
+
+
+def test_refexact_moving_camera_sequence(built_library, oracle):
+    """Non-identity poses under RefExact (geometry is wrong by design, Q1/Q2/Q9, but deterministic)."""
+    cfg = Config(numBuckets=100003, numVoxelBlocks=4000)
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    for k in (0, 10, 20):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        depth = render(cfg, scenes.scene_S1(), pose)
+        ov, _, _ = ot.preprocess(depth)
+        rep, nvis, nupd = ot.fuse_frame(pose, ov)
+        assert rep.bucketsContended == 0
+        v, n, _ = gpu_preprocess(ctx, depth)
+        ctx.fuse_frame(pose, v, n)
+        st = ctx.stats()
+        assert (st.numVisible, int(st.numUpdated), st.lastInserted) == (nvis, nupd, rep.inserted)
+    exact, _ = compare_blocks(ctx.block_dict(), ot.block_dict())
+    assert exact
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_fixed_sequence_bit_exact(built_library, oracle, dense):
+    cfg = fixed_cfg()
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    for k in (0, 5, 10, 15):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        depth = render(cfg, scenes.scene_S1(), pose)
+        ov, _, odf = ot.preprocess(depth)
+        rep, nvis, nupd = ot.fuse_frame(pose, ov, odf if dense else None)
+        assert rep.dropped == 0
+        v, n, df = gpu_preprocess(ctx, depth)
+        ctx.fuse_frame(pose, v, n, df if dense else None)
+        st = ctx.stats()
+        assert entries_to_set(ctx.export_entries()) == entries_to_set(ot.entries())
+        assert (st.numVisible, int(st.numUpdated), st.lastInserted, st.dropped) == (nvis, nupd, rep.inserted, 0)
+    exact, worst = compare_blocks(ctx.block_dict(), ot.block_dict())
+    assert exact, f"Fixed sdf not bit-exact (worst {worst})"
+
+
+def test_fixed_overflow_chain(built_library, oracle):
+    """64 buckets x 2 slots force most blocks into the overflow arena; set equality must survive."""
+    cfg = fixed_cfg(numBuckets=64, bucketSize=2, attachedLinkedListSize=64, overflowSlots=4096, numVoxelBlocks=4096,
+                    width=160, height=120, fx=517.3 / 4, fy=516.5 / 4, cx=318.6 / 4, cy=255.3 / 4)
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    for k in (0, 8):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        depth = render(cfg, scenes.scene_S1(), pose)
+        ov, _, odf = ot.preprocess(depth)
+        rep, nvis, nupd = ot.fuse_frame(pose, ov, odf)
+        assert rep.dropped == 0
+        v, n, df = gpu_preprocess(ctx, depth)
+        ctx.fuse_frame(pose, v, n, df)
+        st = ctx.stats()
+        assert st.overflowUsed > 0 and st.dropped == 0
+        assert entries_to_set(ctx.export_entries()) == entries_to_set(ot.entries())
+        assert (st.numVisible, int(st.numUpdated)) == (nvis, nupd)
+    # chain integrity: every entry reachable from its bucket head through the offsets
+    ent = ctx.export_entries()
+    assert len(entries_to_set(ent)) == len(ent), "duplicate keys in the table"
+    exact, _ = compare_blocks(ctx.block_dict(), ot.block_dict())
+    assert exact
+
+
+def test_fixed_capacity_exhaustion_is_graceful(built_library, oracle):
+    """Heap smaller than the request: no crash, no duplicates, counters consistent (the reference reads
+    out of bounds here, quirk Q6)."""
+    cfg = fixed_cfg(numVoxelBlocks=50)
+    ot = oracle.OracleTable(cfg)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    ov, _, _ = ot.preprocess(depth)
+    ctx = Context(cfg)
+    v, n, df = gpu_preprocess(ctx, depth)
+    ctx.fuse_frame(np.eye(4, dtype=np.float32), v, n, df)
+    st = ctx.stats()
+    ent = ctx.export_entries()
+    ent = ent[ent["ptr"] >= 0]
+    assert st.numAllocated == 50 and len(ent) == 50 and st.dropped > 0
+    assert len(entries_to_set(ent)) == 50
+    assert sorted(int(p) // 512 for p in ent["ptr"]) == list(range(50))
+
+
+@pytest.mark.parametrize("policy", [POLICY_REF_EXACT, POLICY_FIXED])
+def test_icp_system_and_split_kernels(built_library, oracle, policy):
+    cfg = Config(policy=policy, depthMax=4.0, icpNormalThres=0.8 if policy == POLICY_FIXED else -1.0)
+    ot = oracle.OracleTable(cfg)
+    d0 = render(cfg, scenes.scene_S1(), scenes.trajectory_C2(0))
+    d1 = render(cfg, scenes.scene_S1(), scenes.trajectory_C2(20))
+    tv, tn, _ = ot.preprocess(d0)      # target = frame 0
+    iv, inn, _ = ot.preprocess(d1)     # input = frame 20
+    delta = oracle.se3_exp([0.01, -0.004, 0.002, 0.003, -0.002, 0.001])
+    ctx = Context(cfg)
+    g_tv, g_tn, g_iv, g_in = cu(tv), cu(tn), cu(iv), cu(inn)
+
+    # split form: correspondences + Jacobians, bit-exact
+    n = cfg.width * cfg.height
+    corr, corrN = torch.zeros((n, 4), device="cuda"), torch.zeros((n, 4), device="cuda")
+    res, err, J = torch.zeros(n, device="cuda"), torch.zeros(1, device="cuda"), torch.zeros((n, 6), device="cuda")
+    ctx.find_correspondences(g_iv, g_in, g_tv, g_tn, delta, corr, corrN, res, err)
+    ctx.jacobians(corr, corrN, J)
+    torch.cuda.synchronize()
+    oerr, ocorr, ocorrN, ores = oracle.find_correspondences(cfg, iv, inn, tv, tn, delta)
+    assert np.array_equal(bits(corr.cpu().numpy()), bits(ocorr))
+    assert np.array_equal(bits(corrN.cpu().numpy()), bits(ocorrN))
+    assert np.array_equal(bits(res.cpu().numpy()), bits(ores))
+    assert abs(float(err.item()) - float(np.sum(ores.astype(np.float64)))) <= 1e-5 * max(1.0, float(np.sum(np.abs(ores))))
+    assert np.array_equal(bits(J.cpu().numpy()), bits(oracle.jacobians(cfg, ocorr, ocorrN)))
+
+    # fused reduction vs fp64 oracle sums, relative 1e-5 of the system's scale
+    ctx.icp_set_twist(oracle.se3_log(delta))
+    dsys = torch.zeros(32, device="cuda")
+    ctx.icp_reduce(g_iv, g_in, g_tv, g_tn, 0, cfg.height, dsys)
+    torch.cuda.synchronize()
+    gsys = dsys.cpu().numpy()
+    gdelta = ctx.icp_get()[0]
+    osys = oracle.icp_system(cfg, iv, inn, tv, tn, gdelta)
+    assert gsys[28] == osys[28] and gsys[28] > 50000            # same correspondence count
+    scale = float(np.max(np.abs(osys[:21])))
+    assert np.max(np.abs(gsys[:21] - osys[:21])) <= 1e-5 * scale
+    assert np.max(np.abs(gsys[21:27] - osys[21:27])) <= 1e-5 * max(1.0, float(np.max(np.abs(osys[21:27])))) + 1e-5 * scale * 1e-3
+    assert abs(gsys[27] - osys[27]) <= 1e-5 * max(1.0, abs(float(osys[27])))
+    # rows split in two halves (the multi-GPU decomposition) sums to the whole
+    a, b = torch.zeros(32, device="cuda"), torch.zeros(32, device="cuda")
+    ctx.icp_reduce(g_iv, g_in, g_tv, g_tn, 0, 200, a)
+    ctx.icp_reduce(g_iv, g_in, g_tv, g_tn, 200, cfg.height, b)
+    torch.cuda.synchronize()
+    assert np.allclose((a + b).cpu().numpy()[:29], gsys[:29], rtol=2e-5, atol=1e-3)
+    # reduce from stored correspondences (what Solver::BuildLinearSystem gets) agrees with the fused form
+    if policy == POLICY_REF_EXACT:
+        ctx.find_correspondences(g_iv, g_in, g_tv, g_tn, gdelta, corr, corrN, res, err)
+        c = torch.zeros(32, device="cuda")
+        ctx.icp_reduce_corr(corr, corrN, res, c)
+        torch.cuda.synchronize()
+        assert np.allclose(c.cpu().numpy()[:28], gsys[:28], rtol=2e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("policy", [POLICY_REF_EXACT, POLICY_FIXED])
+def test_icp_align_pose(built_library, oracle, policy):
+    """20 Gauss-Newton iterations on the device vs the oracle loop: pose within 1e-4."""
+    cfg = Config(policy=policy)
+    ot = oracle.OracleTable(cfg)
+    T0, T1 = scenes.trajectory_C2(0), scenes.trajectory_C2(12)
+    tv, tn, _ = ot.preprocess(render(cfg, scenes.scene_S1(), T0))
+    iv, inn, _ = ot.preprocess(render(cfg, scenes.scene_S1(), T1))
+    ctx = Context(cfg)
+    ctx.icp_reset(True)
+    ctx.icp_align(cu(iv), cu(inn), cu(tv), cu(tn), 20)
+    gdelta, gtwist, _ = ctx.icp_get()
+    its, oest, odelta = oracle.icp_align(cfg, iv, inn, tv, tn, 20)
+    assert its == 20
+    assert rot_err(gdelta[:3, :3], odelta[:3, :3]) <= 1e-4
+    assert np.max(np.abs(gdelta[:3, 3] - odelta[:3, 3])) <= 1e-4
+    assert np.max(np.abs(gtwist - oest)) <= 1e-4
+    if policy == POLICY_FIXED:       # the corrected pipeline must actually recover the motion
+        truth = np.linalg.inv(T0) @ T1
+        assert rot_err(gdelta[:3, :3], truth[:3, :3]) <= 2e-3
+        assert np.max(np.abs(gdelta[:3, 3] - truth[:3, 3])) <= 5e-3
+    # estimate accumulates across Align calls (quirk Q24): a second call starts from the first result
+    ctx.icp_align(cu(iv), cu(inn), cu(tv), cu(tn), 5)
+    its2, oest2, odelta2 = oracle.icp_align(cfg, iv, inn, tv, tn, 5, oest)
+    g2 = ctx.icp_get()[0]
+    assert rot_err(g2[:3, :3], odelta2[:3, :3]) <= 1e-4 and np.max(np.abs(g2[:3, 3] - odelta2[:3, 3])) <= 1e-4
+
+
+def test_linear_system_300_contract(built_library, oracle):
+    """buildLinearSystemOnDevice (the un-built LinearSystem.cu reducer): 300 x 27 partials whose sum is
+    A^T A | A^T b with A = (s x n, n), b = n.d - n.s."""
+    cfg = Config()
+    ot = oracle.OracleTable(cfg)
+    tv, tn, _ = ot.preprocess(render(cfg, scenes.scene_S1(), scenes.trajectory_C2(0)))
+    iv, _, _ = ot.preprocess(render(cfg, scenes.scene_S1(), scenes.trajectory_C2(10)))
+    lib = L.load_library()
+    n = 640 * 480
+    d_out = torch.zeros(300 * 27, device="cuda")
+    h_out = np.zeros(300 * 27, np.float32)
+    g_iv, g_tv, g_tn = cu(iv), cu(tv), cu(tn)
+    lib.buildLinearSystemOnDevice(g_iv.data_ptr(), g_tv.data_ptr(), g_tn.data_ptr(), d_out.data_ptr(), h_out.ctypes.data)
+    got = h_out.reshape(300, 27).astype(np.float64).sum(0)
+    s, d, nn = iv[:, :3].astype(np.float64), tv[:, :3].astype(np.float64), tn[:, :3].astype(np.float64)
+    A = np.concatenate([np.cross(s, nn), nn], axis=1)
+    b = np.sum(nn * d, 1) - np.sum(nn * s, 1)
+    AtA, Atb = A.T @ A, A.T @ b
+    want = np.concatenate([AtA[np.triu_indices(6)], Atb])
+    assert np.allclose(got, want, rtol=2e-5, atol=1e-5 * np.max(np.abs(want)))
+    assert np.array_equal(h_out, d_out.cpu().numpy())
+
+
+def test_raycast_vs_oracle_and_scene(built_library, oracle):
+    cfg = fixed_cfg(width=320, height=240, fx=517.3 / 2, fy=516.5 / 2, cx=318.6 / 2, cy=255.3 / 2, numVoxelBlocks=4096)
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    for k in range(0, 12, 2):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        depth = render(cfg, scenes.scene_S1(), pose)
+        ov, _, odf = ot.preprocess(depth)
+        ot.fuse_frame(pose, ov, odf)
+        v, n, df = gpu_preprocess(ctx, depth)
+        ctx.fuse_frame(pose, v, n, df)
+    pose = scenes.trajectory_C2(6).astype(np.float32)
+    ctx.set_pose(pose)
+    rv, rn = torch.zeros_like(v), torch.zeros_like(n)
+    ctx.raycast(rv, rn)
+    torch.cuda.synchronize()
+    gv, gn = rv.cpu().numpy(), rn.cpu().numpy()
+    cv, cn = ot.raycast(pose)
+    hit_g, hit_c = gv[:, 2] > 0, cv[:, 2] > 0
+    assert np.mean(hit_g == hit_c) > 0.999
+    both = hit_g & hit_c
+    assert both.sum() > 0.8 * cfg.width * cfg.height
+    assert np.mean(np.abs(gv[both] - cv[both]).max(1) <= 1e-4) > 0.999
+    nb = both & (np.abs(gn).sum(1) > 0) & (np.abs(cn).sum(1) > 0)
+    assert np.mean(np.abs(gn[nb] - cn[nb]).max(1) <= 1e-3) > 0.999
+    # against the analytic scene: depth error below one voxel away from silhouettes
+    truth = render(cfg, scenes.scene_S1(), pose).reshape(-1).astype(np.float64) / cfg.depthScale
+    err = np.abs(gv[:, 2] - truth)[hit_g & (truth > 0)]
+    assert np.median(err) < 0.25 * cfg.voxelSize and np.mean(err < cfg.voxelSize) > 0.97
+    # normals point at the camera (negative z), unit length
+    nz = gn[nb]
+    assert np.all(np.abs(np.linalg.norm(nz[:, :3], axis=1) - 1.0) < 1e-4) and np.mean(nz[:, 2] < 0) > 0.999
+
+
+def test_legacy_entry_points_match_handle_api(built_library, oracle):
+    """The reference's own call sequence (SDF_Hashtable.cpp:60-81 ctor, :11-40 integrate) through the
+    legacy C symbols gives the same table as the handle API and the oracle."""
+    lib = L.load_library()
+    cfg = Config(numBuckets=100003)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    ot = oracle.OracleTable(cfg)
+    ov, on, _ = ot.preprocess(depth)
+    rep, nvis, nupd = ot.fuse_frame(np.eye(4, dtype=np.float32), ov)
+
+    p = cfg.to_c().table
+    K, Kinv = cfg.K(), cfg.Kinv()
+    assert lib.SetCameraIntrinsic(K.ctypes.data, Kinv.ctypes.data)         # CameraTracking.cpp:134
+    lib.updateConstantHashTableParams(C.byref(p))                          # SDF_Hashtable.cpp:75
+    lib.deviceAllocate(C.byref(p))                                         # :76
+    lib.calculateKinectProjectionMatrix()                                  # :79
+    d = cu(depth.reshape(-1))
+    v = torch.zeros((640 * 480, 4), device="cuda")
+    n = torch.zeros((640 * 480, 4), device="cuda")
+    lib.preProcess(v.data_ptr(), n.data_ptr(), d.data_ptr())               # Application.cpp:73
+    assert np.array_equal(bits(v.cpu().numpy()), bits(ov)) and np.array_equal(bits(n.cpu().numpy()), bits(on))
+    lib.mapGLobjectsToCUDApointers(None, None, None)                       # SDF_Hashtable.cpp:13
+    lib.updateConstantHashTableParams(C.byref(p))                          # :21
+    lib.resetHashTableMutexes(C.byref(p))                                  # :24
+    lib.allocBlocks(v.data_ptr(), n.data_ptr())                            # :27
+    count = lib.flattenIntoBuffer(C.byref(p))                              # :30
+    assert count == nvis
+    p.numOccupiedBlocks = count                                            # :32
+    lib.updateConstantHashTableParams(C.byref(p))                          # :33
+    lib.integrateDepthMap(C.byref(p), v.data_ptr())                        # :36
+    # read back through the stand-ins of the three GL buffers
+    cnt = np.zeros(1, np.int32)
+    compact = np.zeros(count, dtype=L.VOXEL_ENTRY_DTYPE)
+    cudart = torch.cuda.cudart()
+    torch.cuda.synchronize()
+    h = C.c_void_p(lib.vhLegacyContext())
+    n_ent = C.c_int(0)
+    L.check(lib.vh_export_compact(h, compact.ctypes.data, count, C.byref(n_ent)))
+    assert n_ent.value == count and entries_to_set(compact) == entries_to_set(ot.compact_entries())
+    blk = np.zeros(512, dtype=L.VOXEL_DTYPE)
+    cpu_blocks = ot.block_dict()
+    for e in compact[:: max(1, count // 16)]:
+        L.check(lib.vh_export_block(h, int(e["ptr"]), blk.ctypes.data))
+        ref = cpu_blocks[(int(e["x"]), int(e["y"]), int(e["z"]))]
+        assert np.array_equal(bits(blk.view(np.float32).reshape(512, 2)), bits(ref))
+    # computeCorrespondences + CalculateJacobiansAndResiduals (CameraTracking.cpp:53, Solver.cpp:74)
+    corr, corrN = torch.zeros((640 * 480, 4), device="cuda"), torch.zeros((640 * 480, 4), device="cuda")
+    res, J = torch.zeros(640 * 480, device="cuda"), torch.zeros((640 * 480, 6), device="cuda")
+    delta = L.Float4x4()
+    dm = oracle.se3_exp([0.005, 0, 0, 0, 0.002, 0]).reshape(16)
+    for i in range(16):
+        delta.entries[i] = float(dm[i])
+    err = lib.computeCorrespondences(v.data_ptr(), v.data_ptr(), n.data_ptr(), corr.data_ptr(), corrN.data_ptr(), res.data_ptr(),
+                                     C.byref(delta), 640, 480)
+    oerr, ocorr, ocorrN, ores = oracle.find_correspondences(cfg, ov, None, ov, on, dm)
+    assert np.array_equal(bits(res.cpu().numpy()), bits(ores)) and abs(err - oerr) <= 1e-4 * max(1.0, abs(oerr))
+    lib.CalculateJacobiansAndResiduals(v.data_ptr(), corr.data_ptr(), corrN.data_ptr(), J.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(J.cpu().numpy()), bits(oracle.jacobians(cfg, ocorr, ocorrN)))
+    lib.deviceFree()
+    del cudart, cnt
+
+
+def test_pipeline_tracks_synthetic_trajectory(built_library, oracle):
+    """Native frame loop (graph replay) on 40 frames of config C2: pose follows the ground truth, and the
+    graph path is bit-identical to plain launches."""
+    cfg = fixed_cfg(numVoxelBlocks=16384, icpNormalThres=0.8)
+    poses = [scenes.trajectory_C2(k) for k in range(40)]
+    frames = [cu(render(cfg, scenes.scene_S1(), p).reshape(-1)) for p in poses]
+    results = []
+    for use_graph in (True, False):
+        ctx = Context(cfg)
+        pipe = FramePipeline(ctx, iterations=10, mode=FramePipeline.FRAME_TO_FRAME, use_graph=use_graph)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            pipe.reset(poses[0].astype(np.float32))
+            for f in frames:
+                pipe.push_device(f)
+            pose = pipe.pose()
+        st = ctx.stats()
+        results.append((pose, st.numAllocated, int(st.numUpdated), pipe.launches()))
+        truth = poses[-1]
+        assert rot_err(pose[:3, :3], truth[:3, :3]) < 5e-3
+        assert np.max(np.abs(pose[:3, 3] - truth[:3, 3])) < 0.01
+        assert st.numAllocated > 300 and st.dropped == 0
+    assert np.array_equal(bits(results[0][0]), bits(results[1][0]))
+    assert results[0][1:3] == results[1][1:3]
+    assert results[0][3] == results[1][3] == 40 + 39 * (10 + 1) + 40 * 3 + 1
+
+
+def test_frame_to_model_tracking(built_library, oracle):
+    """Track-integrate-raycast loop (config C5): ICP target = raycast of the model."""
+    cfg = fixed_cfg(width=320, height=240, fx=517.3 / 2, fy=516.5 / 2, cx=318.6 / 2, cy=255.3 / 2, numVoxelBlocks=16384,
+                    icpNormalThres=0.8)
+    poses = [scenes.trajectory_C2(k) for k in range(30)]
+    ctx = Context(cfg)
+    pipe = FramePipeline(ctx, iterations=10, mode=FramePipeline.FRAME_TO_MODEL, use_graph=True)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        pipe.reset(poses[0].astype(np.float32))
+        for p in poses:
+            pipe.push_device(cu(render(cfg, scenes.scene_S1(), p).reshape(-1)))
+        pose = pipe.pose()
+    assert rot_err(pose[:3, :3], poses[-1][:3, :3]) < 5e-3
+    assert np.max(np.abs(pose[:3, 3] - poses[-1][:3, 3])) < 0.01
+
+
+def test_partition_union_equals_single(built_library, oracle):
+    """owner = mix(block) mod P: the union over ranks equals the single-table result, block by block."""
+    base = fixed_cfg(numVoxelBlocks=4096)
+    depths = [render(base, scenes.scene_S1(), scenes.trajectory_C2(k)) for k in (0, 6)]
+    single = Context(base)
+    parts = [Context(fixed_cfg(numVoxelBlocks=4096, partCount=3, partRank=r)) for r in range(3)]
+    for k, depth in zip((0, 6), depths):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        for c in [single] + parts:
+            v, n, df = gpu_preprocess(c, depth)
+            c.fuse_frame(pose, v, n, df)
+    whole = single.block_dict()
+    union = {}
+    for c in parts:
+        d = c.block_dict()
+        assert not (set(d) & set(union)), "a block is owned by two ranks"
+        union.update(d)
+    exact, _ = compare_blocks(union, whole)
+    assert exact
+    assert all(len(c.export_entries()) > 0.2 * len(whole) for c in parts)
+    # the oracle applies the same ownership rule
+    ot = oracle.OracleTable(fixed_cfg(numVoxelBlocks=4096, partCount=3, partRank=1))
+    for k, depth in zip((0, 6), depths):
+        ov, _, odf = ot.preprocess(depth)
+        ot.fuse_frame(scenes.trajectory_C2(k).astype(np.float32), ov, odf)
+    assert entries_to_set(parts[1].export_entries()) == entries_to_set(ot.entries())
+
+
+def test_checkpoint_roundtrip_and_dump(built_library, oracle, tmp_path):
+    cfg = fixed_cfg(numVoxelBlocks=2048)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    a = Context(cfg)
+    v, n, df = gpu_preprocess(a, depth)
+    a.fuse_frame(np.eye(4, dtype=np.float32), v, n, df)
+    a.save(tmp_path / "model.vhb")
+    b = Context(cfg)
+    b.load(tmp_path / "model.vhb")
+    ex, _ = compare_blocks(b.block_dict(), a.block_dict())
+    assert ex and b.stats().heapCounter == a.stats().heapCounter
+    # the loaded model keeps fusing identically
+    for c in (a, b):
+        c.fuse_frame(np.eye(4, dtype=np.float32), v, n, df)
+    ex, _ = compare_blocks(b.block_dict(), a.block_dict())
+    assert ex
+    a.dump_text(tmp_path / "SDF_dump.txt")                 # format of SDFRenderer.cpp:90-108
+    lines = (tmp_path / "SDF_dump.txt").read_text().splitlines()
+    assert lines[0] == f"numOccupiedBlocks from GL :{a.stats().numVisible}"
+    assert lines[4].startswith("0) : pos : (") and len(lines[5].rstrip("\t").split("\t")) == 512
+
+
+# ---- full-size, size-independent properties (configs C2 / C3) --------------------------------------
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_full_size_properties(built_library, oracle, name):
+    if name == "C2":
+        cfg = fixed_cfg(numVoxelBlocks=65536)
+        scene, traj = scenes.scene_S1(), scenes.trajectory_C2
+    else:
+        cfg = fixed_cfg(width=1280, height=720, fx=1034.6, fy=1033.0, cx=637.2, cy=382.95, voxelSize=0.005, truncation=0.02,
+                        numBuckets=1000003, numVoxelBlocks=262144, overflowSlots=65536, depthMax=8.0, maxIntegrationDistance=8.0)
+        scene, traj = scenes.scene_S2(), lambda k: scenes.trans(0, 0, 0.3) @ scenes.trajectory_C3(k)
+    ctx = Context(cfg)
+    pose = traj(0).astype(np.float32)
+    depth = render(cfg, scene, pose)
+    v, n, df = gpu_preprocess(ctx, depth)
+    ctx.fuse_frame(pose, v, n, df)
+    s1 = ctx.stats()
+    assert s1.numAllocated > 0 and s1.dropped == 0 and s1.numVisible == s1.numAllocated
+    ent = ctx.export_entries()
+    assert len(entries_to_set(ent)) == len(ent) == s1.numAllocated          # no duplicate keys
+    assert sorted(ent["ptr"] // 512) == list(range(cfg.numVoxelBlocks - s1.numAllocated, cfg.numVoxelBlocks))   # heap order (ref :207/:331)
+    # idempotence: allocating the same frame again inserts nothing
+    ctx.fuse_frame(pose, v, n, df)
+    s2 = ctx.stats()
+    assert s2.numAllocated == s1.numAllocated and s2.lastInserted == 0 and s2.numUpdated == s1.numUpdated
+    # weights: every updated voxel saw the same sample twice => sdf unchanged, weight = min(max, 2 w)
+    e = ent[len(ent) // 2]
+    blk = ctx.export_block(int(e["ptr"]))
+    w = blk["weight"][blk["weight"] > 0]
+    assert w.size > 0 and np.all(w >= 2.0) and np.all(w <= cfg.integrationWeightMax)
+    # every pixel's surface voxel is allocated: the block containing each valid vertex is in the table
+    vv = v.cpu().numpy()
+    valid = (vv[:, 2] > cfg.depthMin) & (vv[:, 2] < cfg.depthMax)
+    pw = (vv[valid][::97, :3].astype(np.float64) @ pose[:3, :3].T.astype(np.float64)) + pose[:3, 3]
+    blocks = np.floor((pw / cfg.voxelSize + 0.5) / 8.0).astype(np.int64)
+    have = entries_to_set(ent)
+    missing = sum(tuple(int(c) for c in b) not in have for b in blocks)
+    assert missing <= 0.001 * len(blocks)
+    # oracle cross-check of the counts at full size
+    ot = oracle.OracleTable(cfg)
+    ov, _, odf = ot.preprocess(depth)
+    rep, nvis, nupd = ot.fuse_frame(pose, ov, odf)
+    assert (rep.inserted, nvis, nupd) == (s1.numAllocated, s1.numVisible, int(s1.numUpdated))
+    assert entries_to_set(ent) == entries_to_set(ot.entries())

@@ -1,0 +1,215 @@
+// k_alloc.cu -- per-frame hash-block allocation (north_star (a)).
+// Replaces allocBlocksKernel + insertVoxelEntry + allocSingleBlockInHeap
+// (ref VoxelUtils.cu:328-334, :418-541, :606-716).
+//
+// The reference launches one thread per pixel and lets all ~1500 pixels that see the same block
+// probe the same bucket and fight over the same mutex word.  Here a request goes through three
+// filters before it touches HBM:
+//   1. warp:   __match_any_sync on the block hash, one leader per distinct key;
+//   2. CTA:    a 128-entry shared-memory filter updated with 64-bit atomicExch (a key is dropped
+//              only if the identical key was put there by a thread that went on to stage 3);
+//   3. global: read-only probe of the bucket (one LDG.128 per slot); only a miss goes on to claim.
+// Fixed policy claims a free slot lock-free with ONE 128-bit CAS that publishes the key together
+// with the claim ({INT_MAX^3, FREE} -> {x, y, z, LOCKED}), so a concurrent request for the same
+// block recognises it without waiting; the heap pop and the ptr store follow.  Buckets that are
+// full spill into the overflow arena through a lock-free chain append (CAS on the tail's link).
+// RefExact keeps the reference's rule bit for bit: a per-bucket atomicExch try-lock that is never
+// released inside a frame, so at most one new block per bucket per frame (quirk Q4).
+#include "vh_device.cuh"
+
+namespace vh {
+
+constexpr int kFilterSize = 128;
+constexpr unsigned long long kFilterEmpty = ~0ull;
+
+__device__ __forceinline__ bool packKey(int x, int y, int z, unsigned long long& out) {
+    const int lim = 1 << 20;
+    if (x < -lim || x >= lim || y < -lim || y >= lim || z < -lim || z >= lim) return false;
+    out = ((unsigned long long)(unsigned)(x & 0x1FFFFF)) | ((unsigned long long)(unsigned)(y & 0x1FFFFF) << 21) |
+          ((unsigned long long)(unsigned)(z & 0x1FFFFF) << 42);
+    return true;
+}
+
+__device__ __forceinline__ void finishInsert(const View& v, unsigned slot, int x, int y, int z, bool isArena) {
+    int addr = atomicSub(&v.ctr->heapCounter, 1);           // ref allocSingleBlockInHeap :331
+    if (addr < 0) {                                         // heap exhausted: the reference reads out of bounds here (Q6)
+        atomicAdd(&v.ctr->heapCounter, 1);
+        // in-bucket slot goes back to free; a linked arena entry stays as a tombstone {key, FREE}
+        v.entries[slot] = isArena ? make_int4(x, y, z, VH_FREE_BLOCK) : freeSlot();
+        atomicAdd(&v.ctr->dropped, 1);
+        return;
+    }
+    unsigned id = v.heap[addr];                             // ref :333
+    v.blockInfo[id] = make_int4(x, y, z, (int)slot);
+    reinterpret_cast<volatile int*>(v.entries + slot)[3] = (int)(id * 512u);   // ref :449-451 (ptr = id*512)
+    atomicAdd(&v.ctr->lastInserted, 1);
+}
+
+__device__ void insertFixed(const View& v, int x, int y, int z) {
+    const unsigned h = bucketOf(v, x, y, z);
+    const unsigned base = h * v.bucketSize;
+    const int4 want = make_int4(x, y, z, VH_LOCKED_BLOCK);
+    for (unsigned i = 0; i < v.bucketSize; ++i) {
+        int4 e = ldSlot(v.entries + base + i);
+        if (e.w != VH_FREE_BLOCK) {
+            if (sameKey(e, x, y, z)) return;                // present (or being inserted by a peer)
+            continue;
+        }
+        int4 old;
+        if (casSlot(v.entries + base + i, e, want, old)) { finishInsert(v, base + i, x, y, z, false); return; }
+        if (old.w != VH_FREE_BLOCK && sameKey(old, x, y, z)) return;   // a peer won the slot with the same key
+        if (old.w == VH_FREE_BLOCK) --i;                    // slot changed but is still free (rollback): retry it
+    }
+    // bucket full: walk / extend the overflow chain hanging off the bucket's last slot
+    unsigned cur = base + v.bucketSize - 1;
+    unsigned len = 0;
+    int mySlot = -1;
+    while (true) {
+        int off = *reinterpret_cast<volatile int*>(v.chain + cur);
+        if (off != 0) {
+            cur += (unsigned)off;
+            ++len;
+            int4 e = ldSlot(v.entries + cur);
+            if (sameKey(e, x, y, z) && e.w != VH_FREE_BLOCK) break;   // present; mySlot (if any) is orphaned below
+            continue;
+        }
+        if (len >= v.chainMax) { atomicAdd(&v.ctr->dropped, 1); break; }
+        if (mySlot < 0) {
+            int a = atomicAdd(&v.ctr->overflowUsed, 1);
+            if (a >= (int)v.overflowSlots) { atomicSub(&v.ctr->overflowUsed, 1); atomicAdd(&v.ctr->dropped, 1); return; }
+            mySlot = (int)(v.numSlots + (unsigned)a);
+            v.entries[mySlot] = want;
+            __threadfence();                                // entry visible before it can be reached through the link
+        }
+        int prev = atomicCAS(v.chain + cur, 0, mySlot - (int)cur);
+        if (prev == 0) { finishInsert(v, (unsigned)mySlot, x, y, z, true); return; }
+        // a peer appended first: keep walking from its entry with the same arena slot in hand
+    }
+    if (mySlot >= 0) v.entries[mySlot] = make_int4(x, y, z, VH_FREE_BLOCK);   // never linked: invisible, leaked
+}
+
+__device__ void insertRefExact(const View& v, int x, int y, int z) {
+    const unsigned h = bucketOf(v, x, y, z);
+    const unsigned base = h * v.bucketSize;
+    for (unsigned i = 0; i < v.bucketSize; ++i) {
+        unsigned idx = (base + i) % v.numSlots;                              // ref :437-438
+        int4 e = ldSlot(v.entries + idx);
+        if (sameKey(e, x, y, z) && e.w != VH_FREE_BLOCK) return;             // ref :440-441
+        if (e.w == VH_FREE_BLOCK) {                                          // ref :442
+            int prev = atomicExch(v.mutex + h, VH_LOCKED_BLOCK);             // ref :444
+            if (prev != VH_LOCKED_BLOCK) {                                   // ref :445
+                v.entries[idx] = make_int4(x, y, z, VH_FREE_BLOCK);          // ref :447-448 (pos, offset)
+                int addr = atomicSub(&v.ctr->heapCounter, 1);                // ref :331
+                if (addr < 0) { atomicAdd(&v.ctr->dropped, 1); return; }     // Q6: pos stays written, ptr stays -1
+                unsigned id = v.heap[addr];
+                v.blockInfo[id] = make_int4(x, y, z, (int)idx);
+                reinterpret_cast<volatile int*>(v.entries + idx)[3] = (int)(id * 512u);   // ref :449-451
+                atomicAdd(&v.ctr->lastInserted, 1);
+                return;
+            }
+        }
+    }
+}
+
+// Warp-cooperative request. Must be called by every lane of the warp (converged).
+template <class P>
+__device__ __forceinline__ void warpRequest(const View& v, const float* pose, unsigned long long* filter, bool have, int x, int y, int z) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned mask = __ballot_sync(0xffffffffu, have);
+    if (!have) return;
+    const unsigned h32 = blockHash32(x, y, z);
+    const unsigned peers = __match_any_sync(mask, h32);
+    const int leader = __ffs(peers) - 1;
+    const int lx = __shfl_sync(peers, x, leader), ly = __shfl_sync(peers, y, leader), lz = __shfl_sync(peers, z, leader);
+    const bool same = lx == x && ly == y && lz == z;
+    if ((int)lane != leader && same) return;                // duplicates of the leader's key are done
+    unsigned long long packed;
+    if (packKey(x, y, z, packed)) {
+        unsigned long long old = atomicExch(filter + ((h32 ^ (h32 >> 7)) & (kFilterSize - 1)), packed);
+        if (old == packed) return;                          // already forwarded by this CTA
+    }
+    if (P::fixed) {
+        if (!ownedHere(v, x, y, z)) return;
+        insertFixed(v, x, y, z);
+    } else {
+        if (!refBlockInFrustum(v, pose, x, y, z)) return;   // ref :673; depends on (key, pose) only
+        insertRefExact(v, x, y, z);
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(256) k_alloc(View v, const float4* __restrict__ verts) {
+    __shared__ unsigned long long filter[kFilterSize];
+    __shared__ float sPose[16];
+    for (int i = threadIdx.x; i < kFilterSize; i += 256) filter[i] = kFilterEmpty;
+    if (threadIdx.x < 16) sPose[threadIdx.x] = v.frame->pose[threadIdx.x];
+    __syncthreads();
+
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const bool inside = px < v.W && py < v.H;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) p = __ldg(verts + (size_t)py * v.W + px);
+
+    if (!P::fixed) {
+        // ref :620-636: skip z == 0, transform by global_transform, one block per pixel (Q3)
+        bool have = inside && !(p.z == 0.0f);
+        int3 b = make_int3(0, 0, 0);
+        if (have) {
+            float4 w = mul4(sPose, p.x, p.y, p.z, p.w);
+            b = refWorld2Block(v, w.x, w.y, w.z);
+        }
+        warpRequest<P>(v, sPose, filter, have, b.x, b.y, b.z);
+        return;
+    }
+
+    // Fixed: voxel-block DDA over the truncation band [d - t, d + t] along the viewing ray
+    // (what the reference's commented-out code at :637-703 set out to do).
+    const float d = p.z;
+    bool active = inside && (d > v.depthMin && d < v.depthMax);
+    int cur[3] = {0, 0, 0}, end[3] = {0, 0, 0}, step[3] = {0, 0, 0};
+    float tMax[3] = {0, 0, 0}, tDelta[3] = {0, 0, 0};
+    if (active) {
+        float tr = fmaf(v.truncScale, d, v.truncation);
+        float s0 = (d - tr) / d, s1 = (d + tr) / d;
+        float4 a = mul4(sPose, p.x * s0, p.y * s0, d * s0, 1.0f);
+        float4 b = mul4(sPose, p.x * s1, p.y * s1, d * s1, 1.0f);
+        float ga[3] = {(a.x * v.invVoxelSize + 0.5f) * 0.125f, (a.y * v.invVoxelSize + 0.5f) * 0.125f,
+                       (a.z * v.invVoxelSize + 0.5f) * 0.125f};
+        float gb[3] = {(b.x * v.invVoxelSize + 0.5f) * 0.125f, (b.y * v.invVoxelSize + 0.5f) * 0.125f,
+                       (b.z * v.invVoxelSize + 0.5f) * 0.125f};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float fa = floorf(ga[k]), fb = floorf(gb[k]);
+            cur[k] = f2i(fa); end[k] = f2i(fb);
+            float dir = gb[k] - ga[k];
+            if (dir > 0.0f) { step[k] = 1; tMax[k] = ((fa + 1.0f) - ga[k]) / dir; tDelta[k] = 1.0f / dir; }
+            else if (dir < 0.0f) { step[k] = -1; tMax[k] = (fa - ga[k]) / dir; tDelta[k] = -1.0f / dir; }
+            else { step[k] = 0; tMax[k] = INFINITY; tDelta[k] = INFINITY; }
+        }
+    }
+    for (int iter = 0; iter < 32; ++iter) {
+        if (!__any_sync(0xffffffffu, active)) break;
+        warpRequest<P>(v, sPose, filter, active, cur[0], cur[1], cur[2]);
+        if (active) {
+            if (cur[0] == end[0] && cur[1] == end[1] && cur[2] == end[2]) active = false;
+            else {
+                int ax = (tMax[0] <= tMax[1] && tMax[0] <= tMax[2]) ? 0 : (tMax[1] <= tMax[2] ? 1 : 2);
+                float tm = ax == 0 ? tMax[0] : (ax == 1 ? tMax[1] : tMax[2]);
+                if (tm > 1.0f) active = false;
+                else if (ax == 0) { cur[0] += step[0]; tMax[0] += tDelta[0]; }
+                else if (ax == 1) { cur[1] += step[1]; tMax[1] += tDelta[1]; }
+                else { cur[2] += step[2]; tMax[2] += tDelta[2]; }
+            }
+        }
+    }
+}
+
+cudaError_t launch_alloc(vh_context* c, const float4* verts, cudaStream_t s) {
+    dim3 grid((c->v.W + 31) / 32, (c->v.H + 7) / 8);
+    if (c->cfg.policy == VH_POLICY_FIXED) k_alloc<Fixed><<<grid, 256, 0, s>>>(c->v, verts);
+    else k_alloc<RefExact><<<grid, 256, 0, s>>>(c->v, verts);
+    return cudaGetLastError();
+}
+
+}  // namespace vh

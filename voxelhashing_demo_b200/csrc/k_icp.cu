@@ -1,0 +1,457 @@
+// k_icp.cu -- point-to-plane ICP (north_star (d)).
+// Replaces FindCorrespondences (ref CameraTrackingUtils.cu:131-216), CalculateJacAndResKernel
+// (ref Solver.cu:39-71), the cuBLAS Sgemv/Ssyrk pair and the Eigen solve of
+// Solver::BuildLinearSystem (ref Solver.cpp:74-111), SE3Exp/SE3Log (ref SE3.cpp:4-19) and the dead
+// shared-memory reducer buildLinearSystem (ref LinearSystem.cu:24-101).
+//
+// One Gauss-Newton iteration = ONE kernel: projective association, signed point-to-plane
+// residual, the 6-float Jacobian row, 21 + 6 (+2) partial sums kept in registers, warp-shuffle
+// tree, one shared-memory stage per CTA, per-CTA partials to HBM, and the LAST CTA to arrive
+// (ticket) sums the partials in CTA order in fp64 (deterministic), solves the 6x6 system and
+// left-multiplies the SE(3) update into the delta transform -- all on the device, so a 20-iteration
+// Align is 20 back-to-back launches with no host round trip.  The reference moves ~268 B per pixel
+// per iteration through a 7.4 MB Jacobian; this moves the algorithmic 48 B.
+#include "vh_device.cuh"
+
+namespace vh {
+
+struct Corr { bool ok; float3 q, n, p; float d; };
+
+template <class P>
+__device__ __forceinline__ Corr associate(const View& v, const float* __restrict__ delta, const float4* __restrict__ in,
+                                          const float4* __restrict__ inN, const float4* __restrict__ tg,
+                                          const float4* __restrict__ tgN, int idx) {
+    Corr r;
+    r.ok = false;
+    const float4 s = __ldg(in + idx);
+    if (!P::fixed) {
+        if (!(s.z != 0)) return r;                                              // ref :153
+        float4 p = mul4(delta, s.x, s.y, s.z, 1.0f);                            // ref :154-155
+        float3 sp = mul3(v.K, p.x, p.y, p.z);                                   // ref :124
+        int ix = d2i((double)(sp.x / sp.z) + 0.5), iy = d2i((double)(sp.y / sp.z) + 0.5);   // ref :128 (Q20)
+        if (!(ix > 0 && iy > 0 && ix < v.W && iy < v.H)) return r;              // ref :162
+        const float4 q = __ldg(tg + (size_t)iy * v.W + ix);
+        const float4 n = __ldg(tgN + (size_t)iy * v.W + ix);
+        float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;                   // ref :168
+        float d = dx * n.x + dy * n.y + dz * n.z;                               // ref :169
+        if (!(d < v.icpDistThres)) return r;                                    // ref :170 (signed, Q21)
+        r.ok = true; r.q = make_float3(q.x, q.y, q.z); r.n = make_float3(n.x, n.y, n.z);
+        r.p = make_float3(p.x, p.y, p.z); r.d = d;
+        return r;
+    }
+    if (!(s.z > 0.0f)) return r;
+    float4 p = mul4(delta, s.x, s.y, s.z, 1.0f);
+    if (!(p.z > 0.0f)) return r;
+    float u = (v.fx * p.x + v.cx * p.z) / p.z, w = (v.fy * p.y + v.cy * p.z) / p.z;
+    if (!(u >= -0.5f && u < (float)v.W - 0.5f && w >= -0.5f && w < (float)v.H - 0.5f)) return r;
+    int ix = min((int)(u + 0.5f), v.W - 1), iy = min((int)(w + 0.5f), v.H - 1);
+    const float4 q = __ldg(tg + (size_t)iy * v.W + ix);
+    if (!(q.z > 0.0f)) return r;
+    const float4 n = __ldg(tgN + (size_t)iy * v.W + ix);
+    float nn = n.x * n.x + n.y * n.y + n.z * n.z;
+    if (!(nn > 0.0f)) return r;
+    float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+    float e2 = dx * dx + dy * dy + dz * dz;
+    float lim = 3.0f * v.icpDistThres;
+    if (!(e2 < lim * lim)) return r;
+    float d = dx * n.x + dy * n.y + dz * n.z;
+    if (!(fabsf(d) < v.icpDistThres)) return r;
+    if (inN != nullptr && v.icpNormalThres > -1.0f) {
+        const float4 m = __ldg(inN + idx);
+        float rx = delta[0] * m.x + delta[1] * m.y + delta[2] * m.z;
+        float ry = delta[4] * m.x + delta[5] * m.y + delta[6] * m.z;
+        float rz = delta[8] * m.x + delta[9] * m.y + delta[10] * m.z;
+        float cosang = rx * n.x + ry * n.y + rz * n.z;
+        if (!(cosang > v.icpNormalThres)) return r;
+    }
+    r.ok = true; r.q = make_float3(q.x, q.y, q.z); r.n = make_float3(n.x, n.y, n.z);
+    r.p = make_float3(p.x, p.y, p.z); r.d = d;
+    return r;
+}
+
+// 29 running sums: 21 upper-triangle JtJ (row by row), 6 Jtr, residual sum, count.
+// Unknown order (v, omega) as in the live reference path (Solver.cu:29-34, SE3.cpp:6-9).
+__device__ __forceinline__ void accumulate(float* acc, const float* J, float r) {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) acc[k++] += J[i] * J[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[21 + i] += J[i] * r;
+    acc[27] += r;
+    acc[28] += 1.0f;
+}
+
+// CTA reduction of 29 sums; result valid in warp 0 lane k (k < 29) as the return value.
+__device__ __forceinline__ float blockReduce29(float* acc, float (*sm)[32]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 29; ++k) {
+        float s = warpSum(acc[k]);
+        if (lane == 0) sm[warp][k] = s;
+    }
+    __syncthreads();
+    float tot = 0.f;
+    if (warp == 0 && lane < 29) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 0; w < nw; ++w) tot += sm[w][lane];
+    }
+    return tot;
+}
+
+// ---- SE(3) pieces, fp64, closed form (Eigen's matrix exp/log are not available) ----
+__device__ void soTerms(const double* w, double& A, double& B, double& C) {
+    double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    double th = sqrt(t2);
+    if (th < 1e-6) { A = 1.0 - t2 / 6.0; B = 0.5 - t2 / 24.0; C = 1.0 / 6.0 - t2 / 120.0; }
+    else { double s, c; sincos(th, &s, &c); A = s / th; B = (1.0 - c) / t2; C = (th - s) / (t2 * th); }
+}
+__device__ void se3Exp(const double* tw, double* M) {          // ref SE3Exp, twist = (v, omega)
+    const double* vv = tw; const double* w = tw + 3;
+    double A, B, C;
+    soTerms(w, A, B, C);
+    double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double K2[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) K2[i * 3 + j] = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
+    for (int i = 0; i < 3; ++i) {
+        double t = 0;
+        for (int j = 0; j < 3; ++j) {
+            double I = (i == j) ? 1.0 : 0.0;
+            M[i * 4 + j] = I + A * K[i * 3 + j] + B * K2[i * 3 + j];
+            t += (I + B * K[i * 3 + j] + C * K2[i * 3 + j]) * vv[j];
+        }
+        M[i * 4 + 3] = t;
+    }
+    M[12] = M[13] = M[14] = 0; M[15] = 1;
+}
+__device__ void se3Log(const double* M, double* tw) {          // ref SE3Log
+    double tr = M[0] + M[5] + M[10];
+    double cs = fmin(1.0, fmax(-1.0, (tr - 1.0) * 0.5));
+    double th = acos(cs);
+    double f = (th < 1e-6) ? 0.5 + th * th / 12.0 : th / (2.0 * sin(th));
+    double w[3] = {f * (M[9] - M[6]), f * (M[2] - M[8]), f * (M[4] - M[1])};
+    double A, B, C;
+    soTerms(w, A, B, C);
+    double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    double D = (t2 < 1e-12) ? (1.0 / 12.0 + t2 / 720.0) : (1.0 - A / (2.0 * B)) / t2;
+    double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double K2[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) K2[i * 3 + j] = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
+    double t[3] = {M[3], M[7], M[11]};
+    for (int i = 0; i < 3; ++i) {
+        double s = 0;
+        for (int j = 0; j < 3; ++j) s += (((i == j) ? 1.0 : 0.0) - 0.5 * K[i * 3 + j] + D * K2[i * 3 + j]) * t[j];
+        tw[i] = s;
+    }
+    tw[3] = w[0]; tw[4] = w[1]; tw[5] = w[2];
+}
+// x = A^-1 b by Gaussian elimination with partial pivoting (stands in for JTJ.inverse(), Solver.cpp:109)
+__device__ bool solve6(double (*M)[7], double* x) {
+    for (int k = 0; k < 6; ++k) {
+        int p = k;
+        for (int i = k + 1; i < 6; ++i) if (fabs(M[i][k]) > fabs(M[p][k])) p = i;
+        if (!(fabs(M[p][k]) > 1e-300)) return false;
+        if (p != k) for (int j = 0; j < 7; ++j) { double t = M[p][j]; M[p][j] = M[k][j]; M[k][j] = t; }
+        for (int i = k + 1; i < 6; ++i) {
+            double f = M[i][k] / M[k][k];
+            for (int j = k; j < 7; ++j) M[i][j] -= f * M[k][j];
+        }
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = M[i][6];
+        for (int j = i + 1; j < 6; ++j) s -= M[i][j] * x[j];
+        x[i] = s / M[i][i];
+    }
+    for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) return false;
+    return true;
+}
+
+struct IcpDev {               // device-resident solver state (Solver::estimate / deltaTransform)
+    double D[16];             // delta in fp64
+};
+
+// update = -(JtJ)^-1 Jtr; delta <- exp(update) * delta  (== exp(log(exp(update) exp(estimate))), Solver.cpp:110-111)
+__device__ void solveAndUpdate(const float* sys, IcpState* st, IcpDev* dev, Counters* ctr, bool fixedPolicy) {
+    if (fixedPolicy ? !(sys[28] >= 6.0f) : (sys[27] == 0.0f)) { ctr->icpConverged = 1; return; }   // CameraTracking.cpp:55-58
+    double M[6][7], x[6];
+    int k = 0;
+    for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 6; ++j) { M[i][j] = sys[k]; M[j][i] = sys[k]; ++k; }
+    for (int i = 0; i < 6; ++i) M[i][6] = -(double)sys[21 + i];
+    if (!solve6(M, x)) { ctr->icpConverged = 1; return; }
+    double U[16], Pn[16];
+    se3Exp(x, U);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            Pn[i * 4 + j] = U[i * 4] * dev->D[j] + U[i * 4 + 1] * dev->D[4 + j] + U[i * 4 + 2] * dev->D[8 + j] + U[i * 4 + 3] * dev->D[12 + j];
+    for (int i = 0; i < 16; ++i) { dev->D[i] = Pn[i]; st->delta[i] = (float)Pn[i]; }
+    st->iterations += 1;
+}
+
+__device__ __forceinline__ IcpDev* devOf(IcpState* st) { return reinterpret_cast<IcpDev*>(st + 1); }
+
+// Tail shared by the reductions: last CTA sums the partials in CTA order and (optionally) solves.
+__device__ void reduceTail(const View& v, IcpState* st, float* partials, float tot, vh_icp_system* out, bool solve,
+                           bool fixedPolicy) {
+    __shared__ bool isLast;
+    __shared__ float sSys[32];
+    if (threadIdx.x < 32) partials[(size_t)blockIdx.x * 32 + threadIdx.x] = threadIdx.x < 29 ? tot : 0.f;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) isLast = atomicAdd(&v.ctr->icpTicket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        double s = 0;
+        if (threadIdx.x < 29)
+            for (unsigned b = 0; b < gridDim.x; ++b) s += (double)__ldcg(partials + (size_t)b * 32 + threadIdx.x);
+        sSys[threadIdx.x] = (float)s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        st->system[threadIdx.x] = sSys[threadIdx.x];
+        if (out) reinterpret_cast<float*>(out)[threadIdx.x] = sSys[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+        v.ctr->icpTicket = 0;
+        if (solve) solveAndUpdate(sSys, st, devOf(st), v.ctr, fixedPolicy);
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(256) k_icp_iter(View v, IcpState* st, float* partials, const float4* __restrict__ in,
+                                                  const float4* __restrict__ inN, const float4* __restrict__ tg,
+                                                  const float4* __restrict__ tgN, int row0, int row1, vh_icp_system* out,
+                                                  int solve, int first) {
+    __shared__ float sDelta[16];
+    __shared__ float sm[8][32];
+    if (!first && v.ctr->icpConverged) return;                 // uniform: the flag only changes in a tail
+    if (threadIdx.x < 16) sDelta[threadIdx.x] = st->delta[threadIdx.x];
+    __syncthreads();
+    float acc[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+    const int begin = row0 * v.W, end = row1 * v.W;
+    for (int i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+        Corr c = associate<P>(v, sDelta, in, inN, tg, tgN, i);
+        if (!c.ok) continue;
+        const float3 a = P::fixed ? c.p : c.q;                 // ref Solver.cu:26 uses the TARGET point (Q23)
+        float J[6] = {c.n.x, c.n.y, c.n.z, a.y * c.n.z - a.z * c.n.y, a.z * c.n.x - a.x * c.n.z, a.x * c.n.y - a.y * c.n.x};
+        accumulate(acc, J, c.d);
+    }
+    float tot = blockReduce29(acc, sm);
+    if (first && threadIdx.x == 0 && blockIdx.x == 0) v.ctr->icpConverged = 0;
+    reduceTail(v, st, partials, tot, out, solve != 0, P::fixed);
+}
+
+// Normal equations from stored correspondences (the arrays computeCorrespondences leaves behind):
+// what Solver::BuildLinearSystem computes with Sgemv/Ssyrk (ref Solver.cpp:80-94).
+__global__ void __launch_bounds__(256) k_reduce_corr(View v, IcpState* st, float* partials, const float4* __restrict__ corr,
+                                                     const float4* __restrict__ corrN, const float* __restrict__ res,
+                                                     vh_icp_system* out) {
+    __shared__ float sm[8][32];
+    float acc[29];
+#pragma unroll
+    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+    const int n = v.W * v.H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 d = __ldg(corr + i), m = __ldg(corrN + i);
+        const float r = __ldg(res + i);
+        float J[6] = {m.x, m.y, m.z, d.y * m.z - d.z * m.y, d.z * m.x - d.x * m.z, d.x * m.y - d.y * m.x};   // ref Solver.cu:25-34
+        accumulate(acc, J, r);
+        if (m.x == 0.f && m.y == 0.f && m.z == 0.f) acc[28] -= 1.0f;    // empty rows do not count as correspondences
+    }
+    float tot = blockReduce29(acc, sm);
+    reduceTail(v, st, partials, tot, out, false, false);
+}
+
+// Legacy split form of one iteration's first half (ref FindCorrespondences + the three thrust::fill).
+template <class P>
+__global__ void __launch_bounds__(256) k_find_corr(View v, Pose16f delta, const float4* __restrict__ in, const float4* __restrict__ inN,
+                                                   const float4* __restrict__ tg, const float4* __restrict__ tgN,
+                                                   float4* __restrict__ corr, float4* __restrict__ corrN, float* __restrict__ res,
+                                                   float* err) {
+    __shared__ float sDelta[16];
+    __shared__ float sErr[8];
+    if (threadIdx.x < 16) sDelta[threadIdx.x] = delta.m[threadIdx.x];
+    __syncthreads();
+    const int n = v.W * v.H;
+    float e = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Corr c = associate<P>(v, sDelta, in, inN, tg, tgN, i);
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f), m = q;
+        float r = 0.f;
+        if (c.ok) { q = make_float4(c.q.x, c.q.y, c.q.z, 0.f); m = make_float4(c.n.x, c.n.y, c.n.z, 0.f); r = c.d; e += c.d; }
+        corr[i] = q; corrN[i] = m; res[i] = r;                  // ref :176-178 (+ fills :201-203)
+    }
+    e = warpSum(e);
+    if ((threadIdx.x & 31) == 0) sErr[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sErr[w];
+        atomicAdd(err, t);                                      // ref :175, one per CTA instead of one per pixel
+    }
+}
+
+// ref CalculateJacAndResKernel, Solver.cu:39-51 (also covers the zero fill at :67)
+__global__ void k_jacobians(View v, const float4* __restrict__ corr, const float4* __restrict__ corrN, float* __restrict__ J) {
+    const int n = v.W * v.H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 d = __ldg(corr + i), m = __ldg(corrN + i);
+        float* o = J + (size_t)i * 6;
+        o[0] = m.x; o[1] = m.y; o[2] = m.z;
+        o[3] = d.y * m.z - d.z * m.y; o[4] = d.z * m.x - d.x * m.z; o[5] = d.x * m.y - d.y * m.x;
+    }
+}
+
+// The reducer of the un-built LinearSystem.cu:24-90, same output contract: CTA b covers pixels
+// [1024 b, 1024 (b+1)), writes 27 floats: 21 upper-triangle AtA, 6 Atb, with A = (s x n, n),
+// b = n.d - n.s, validity n.w != -inf.  (Unknown order (omega, v) here, unlike the live path.)
+__global__ void __launch_bounds__(128) k_linear_system_300(int n, const float4* __restrict__ in, const float4* __restrict__ corr,
+                                                           const float4* __restrict__ corrN, float* __restrict__ out) {
+    __shared__ float sm[4][32];
+    float acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    const int base = blockIdx.x * 1024 + threadIdx.x * 8;       // WINDOW_SIZE = 8, ref :28-30
+    for (int t = 0; t < 8; ++t) {
+        int i = base + t;
+        if (i >= n) break;
+        const float4 s = __ldg(in + i), d = __ldg(corr + i), m = __ldg(corrN + i);
+        if (m.w == __int_as_float(0xff800000)) continue;        // isValid, ref :12-15
+        float b = (m.x * d.x + m.y * d.y + m.z * d.z) - (m.x * s.x + m.y * s.y + m.z * s.z);   // ref :18-20
+        float A[6] = {s.y * m.z - s.z * m.y, s.z * m.x - s.x * m.z, s.x * m.y - s.y * m.x, m.x, m.y, m.z};   // ref :47-54
+        int k = 0;
+#pragma unroll
+        for (int i2 = 0; i2 < 6; ++i2) {
+#pragma unroll
+            for (int j = i2; j < 6; ++j) acc[k++] += A[i2] * A[j];
+            acc[21 + i2] += A[i2] * b;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        float s = warpSum(acc[k]);
+        if (lane == 0) sm[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) out[blockIdx.x * 27 + threadIdx.x] = sm[0][threadIdx.x] + sm[1][threadIdx.x] + sm[2][threadIdx.x] + sm[3][threadIdx.x];
+}
+
+__global__ void k_icp_solve(View v, IcpState* st, const vh_icp_system* sys, int fixedPolicy) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (v.ctr->icpConverged) return;
+    float s[32];
+    for (int i = 0; i < 32; ++i) s[i] = reinterpret_cast<const float*>(sys)[i];
+    for (int i = 0; i < 32; ++i) st->system[i] = s[i];
+    solveAndUpdate(s, st, devOf(st), v.ctr, fixedPolicy != 0);
+}
+
+struct Twist6 { float t[6]; };
+
+__global__ void k_icp_reset(View v, IcpState* st, int resetDelta, int useTwist, Twist6 tw) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    v.ctr->icpConverged = 0;
+    v.ctr->icpTicket = 0;
+    IcpDev* dev = devOf(st);
+    if (useTwist) {
+        double t[6];
+        for (int i = 0; i < 6; ++i) t[i] = tw.t[i];
+        se3Exp(t, dev->D);
+        for (int i = 0; i < 16; ++i) st->delta[i] = (float)dev->D[i];
+        for (int i = 0; i < 6; ++i) st->twist[i] = tw.t[i];
+    } else if (resetDelta) {
+        for (int i = 0; i < 16; ++i) { dev->D[i] = (i % 5 == 0) ? 1.0 : 0.0; st->delta[i] = (i % 5 == 0) ? 1.f : 0.f; }
+        for (int i = 0; i < 6; ++i) st->twist[i] = 0.f;
+        st->iterations = 0;
+    }
+}
+
+__global__ void k_icp_twist(IcpState* st) {                    // Solver::estimate = SE3Log(delta)
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double tw[6];
+    se3Log(devOf(st)->D, tw);
+    for (int i = 0; i < 6; ++i) st->twist[i] = (float)tw[i];
+}
+
+static int icpGrid(const vh_context* c, int pixels) {
+    int g = (pixels + 255) / 256;
+    int cap = c->numSMs * 2;
+    if (cap > kIcpMaxBlocks) cap = kIcpMaxBlocks;
+    if (g > cap) g = cap;
+    return g < 1 ? 1 : g;
+}
+
+cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
+                            int row0, int row1, vh_icp_system* d_out, bool solve, cudaStream_t s) {
+    return launch_icp_iter_ex(c, in, inN, tg, tgN, row0, row1, d_out, solve, false, s);
+}
+
+cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
+                               int row0, int row1, vh_icp_system* d_out, bool solve, bool first, cudaStream_t s) {
+    int g = icpGrid(c, (row1 - row0) * c->v.W);
+    if (c->cfg.policy == VH_POLICY_FIXED)
+        k_icp_iter<Fixed><<<g, 256, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first);
+    else
+        k_icp_iter<RefExact><<<g, 256, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_icp_solve(vh_context* c, const vh_icp_system* d_sys, cudaStream_t s) {
+    k_icp_solve<<<1, 32, 0, s>>>(c->v, c->icp, d_sys, c->cfg.policy == VH_POLICY_FIXED);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_icp_reset(vh_context* c, bool resetDelta, cudaStream_t s) {
+    Twist6 t{};
+    k_icp_reset<<<1, 32, 0, s>>>(c->v, c->icp, resetDelta ? 1 : 0, 0, t);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_icp_set_twist(vh_context* c, const float* twist6, cudaStream_t s) {
+    Twist6 t;
+    for (int i = 0; i < 6; ++i) t.t[i] = twist6[i];
+    k_icp_reset<<<1, 32, 0, s>>>(c->v, c->icp, 0, 1, t);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_icp_twist(vh_context* c, cudaStream_t s) {
+    k_icp_twist<<<1, 32, 0, s>>>(c->icp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_find_corr(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
+                             const float* delta16_host, float4* corr, float4* corrN, float* res, float* d_err, cudaStream_t s) {
+    Pose16f d;
+    for (int i = 0; i < 16; ++i) d.m[i] = delta16_host[i];
+    cudaError_t e = cudaMemsetAsync(d_err, 0, sizeof(float), s);     // ref :193
+    if (e != cudaSuccess) return e;
+    int g = icpGrid(c, c->v.W * c->v.H);
+    if (c->cfg.policy == VH_POLICY_FIXED) k_find_corr<Fixed><<<g, 256, 0, s>>>(c->v, d, in, inN, tg, tgN, corr, corrN, res, d_err);
+    else k_find_corr<RefExact><<<g, 256, 0, s>>>(c->v, d, in, inN, tg, tgN, corr, corrN, res, d_err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_jacobians(vh_context* c, const float4* corr, const float4* corrN, float* J, cudaStream_t s) {
+    k_jacobians<<<icpGrid(c, c->v.W * c->v.H), 256, 0, s>>>(c->v, corr, corrN, J);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_corr(vh_context* c, const float4* corr, const float4* corrN, const float* res, vh_icp_system* d_out,
+                               cudaStream_t s) {
+    k_reduce_corr<<<icpGrid(c, c->v.W * c->v.H), 256, 0, s>>>(c->v, c->icp, c->icpPartials, corr, corrN, res, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_linear_system_300(vh_context* c, const float4* in, const float4* corr, const float4* corrN, float* d_out,
+                                     cudaStream_t s) {
+    int n = c->v.W * c->v.H;
+    k_linear_system_300<<<(n + 1023) / 1024, 128, 0, s>>>(n, in, corr, corrN, d_out);
+    return cudaGetLastError();
+}
+
+}  // namespace vh

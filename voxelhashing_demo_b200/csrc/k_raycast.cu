@@ -1,0 +1,112 @@
+// k_raycast.cu -- CUDA raycaster over the hash table (north_star (e)).
+// Replaces the non-working GLSL pass shaders/raycastSDF.frag:121-177,189-222 (intent in
+// notes.md:9-16): it produces what the reference never did -- a vertex map and a normal map in the
+// camera frame, with the conventions of preProcess (w = 1 / w = 0, invalid = zeros), so
+// CameraTracking::Align can track frame-to-model.  Fixed policy only: the RefExact TSDF is not a
+// usable surface (quirks Q1, Q9).
+//
+// Latency-bound (dependent hash probes + 8-tap gathers, all L2-resident): one thread per pixel,
+// a one-entry block cache per thread (consecutive samples hit the same block), block-sized steps
+// through unallocated space, TSDF-scaled steps inside the band, linear zero-crossing refinement,
+// central-difference gradient for the normal.
+#include "vh_device.cuh"
+
+namespace vh {
+
+struct BlockCache { int x, y, z; const Voxel* vox; bool valid; };
+
+__device__ __forceinline__ bool voxelAt(const View& v, BlockCache& bc, int vx, int vy, int vz, float& sdf) {
+    const int bx = vx >> 3, by = vy >> 3, bz = vz >> 3;           // floor division by 8
+    if (!(bc.valid && bc.x == bx && bc.y == by && bc.z == bz)) {
+        int ptr = lookupBlock(v, bx, by, bz);
+        bc.x = bx; bc.y = by; bc.z = bz; bc.valid = true;
+        bc.vox = ptr >= 0 ? v.voxels + ptr : nullptr;
+    }
+    if (bc.vox == nullptr) return false;
+    const float2 sw = __ldg(reinterpret_cast<const float2*>(bc.vox + (((vz & 7) * 64) + ((vy & 7) * 8) + (vx & 7))));
+    sdf = sw.x;
+    return sw.y > 0.0f;
+}
+
+__device__ __forceinline__ bool sampleTrilinear(const View& v, BlockCache& bc, float px, float py, float pz, float& out) {
+    const float gx = px * v.invVoxelSize, gy = py * v.invVoxelSize, gz = pz * v.invVoxelSize;
+    const float fx0 = floorf(gx), fy0 = floorf(gy), fz0 = floorf(gz);
+    const int x0 = f2i(fx0), y0 = f2i(fy0), z0 = f2i(fz0);
+    const float ax = gx - fx0, ay = gy - fy0, az = gz - fz0;
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (!voxelAt(v, bc, x0 + (k & 1), y0 + ((k >> 1) & 1), z0 + (k >> 2), s[k])) return false;
+    const float c00 = fmaf(ax, s[1] - s[0], s[0]), c10 = fmaf(ax, s[3] - s[2], s[2]);
+    const float c01 = fmaf(ax, s[5] - s[4], s[4]), c11 = fmaf(ax, s[7] - s[6], s[6]);
+    const float c0 = fmaf(ay, c10 - c00, c00), c1 = fmaf(ay, c11 - c01, c01);
+    out = fmaf(az, c1 - c0, c0);
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_raycast(View v, float4* __restrict__ verts, float4* __restrict__ normals) {
+    __shared__ float sPose[16];
+    if (threadIdx.x < 16) sPose[threadIdx.x] = v.frame->pose[threadIdx.x];
+    __syncthreads();
+    // 16x8 pixel tile per CTA: neighbouring rays walk through the same blocks
+    const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 4);
+    if (x >= v.W || y >= v.H) return;
+    const size_t idx = (size_t)y * v.W + x;
+    const float vs = v.voxelSize, coarse = 4.0f * v.voxelSize;
+    const float3 rd = mul3(v.Kinv, (float)x, (float)y, 1.0f);      // camera ray with z = 1, as preProcess
+    const float dwx = sPose[0] * rd.x + sPose[1] * rd.y + sPose[2] * rd.z;
+    const float dwy = sPose[4] * rd.x + sPose[5] * rd.y + sPose[6] * rd.z;
+    const float dwz = sPose[8] * rd.x + sPose[9] * rd.y + sPose[10] * rd.z;
+    const float ox = sPose[3], oy = sPose[7], oz = sPose[11];
+    BlockCache bc{0, 0, 0, nullptr, false};
+    float z = v.depthMin, zPrev = 0.f, sPrev = 0.f, zHit = 0.f;
+    bool havePrev = false, hit = false;
+    for (int it = 0; it < 4096 && z < v.depthMax; ++it) {
+        const float px = fmaf(z, dwx, ox), py = fmaf(z, dwy, oy), pz = fmaf(z, dwz, oz);
+        float s;
+        if (sampleTrilinear(v, bc, px, py, pz, s)) {
+            if (havePrev && sPrev > 0.0f && s <= 0.0f) {
+                zHit = zPrev + (z - zPrev) * (sPrev / (sPrev - s));
+                hit = true;
+                break;
+            }
+            zPrev = z; sPrev = s; havePrev = true;
+            z += fmaxf(vs, 0.8f * s);
+        } else {
+            havePrev = false;
+            float dummy;
+            const int vx = f2i(floorf(px * v.invVoxelSize + 0.5f)), vy = f2i(floorf(py * v.invVoxelSize + 0.5f)),
+                      vz = f2i(floorf(pz * v.invVoxelSize + 0.5f));
+            voxelAt(v, bc, vx, vy, vz, dummy);
+            z += (bc.vox != nullptr) ? vs : coarse;
+        }
+    }
+    float4 vo = make_float4(0.f, 0.f, 0.f, 1.0f), no = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hit) {
+        const float hx = fmaf(zHit, dwx, ox), hy = fmaf(zHit, dwy, oy), hz = fmaf(zHit, dwz, oz);
+        vo = make_float4(rd.x * zHit, rd.y * zHit, rd.z * zHit, 1.0f);
+        float gxp, gxm, gyp, gym, gzp, gzm;
+        const bool ok = sampleTrilinear(v, bc, hx + vs, hy, hz, gxp) && sampleTrilinear(v, bc, hx - vs, hy, hz, gxm) &&
+                        sampleTrilinear(v, bc, hx, hy + vs, hz, gyp) && sampleTrilinear(v, bc, hx, hy - vs, hz, gym) &&
+                        sampleTrilinear(v, bc, hx, hy, hz + vs, gzp) && sampleTrilinear(v, bc, hx, hy, hz - vs, gzm);
+        if (ok) {
+            const float gx = gxp - gxm, gy = gyp - gym, gz = gzp - gzm;
+            const float cxn = sPose[0] * gx + sPose[4] * gy + sPose[8] * gz;     // R^T g: world -> camera
+            const float cyn = sPose[1] * gx + sPose[5] * gy + sPose[9] * gz;
+            const float czn = sPose[2] * gx + sPose[6] * gy + sPose[10] * gz;
+            const float l = sqrtf(cxn * cxn + cyn * cyn + czn * czn);
+            if (l > 0.0f) no = make_float4(cxn / l, cyn / l, czn / l, 0.0f);
+        }
+    }
+    verts[idx] = vo;
+    normals[idx] = no;
+}
+
+cudaError_t launch_raycast(vh_context* c, float4* verts, float4* normals, cudaStream_t s) {
+    dim3 grid((c->v.W + 15) / 16, (c->v.H + 7) / 8);
+    k_raycast<<<grid, 128, 0, s>>>(c->v, verts, normals);
+    return cudaGetLastError();
+}
+
+}  // namespace vh

@@ -1,0 +1,126 @@
+// vh_internal.h -- context, device views and launch declarations shared by the .cu files.
+// Not installed; the public surface is include/vh/abi.h.
+#ifndef VH_INTERNAL_H
+#define VH_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vh/abi.h"
+
+namespace vh {
+
+// ---- HBM layout --------------------------------------------------------------------------------
+// entries   int4[S + O]       hash slots {x, y, z, ptr}: 16-byte aligned so a slot is read with one
+//                             128-bit load and claimed with one 128-bit CAS (ATOMG.E.CAS.128).
+//                             S = numBuckets*bucketSize in-bucket slots, then O overflow-arena slots.
+// chain     int[S + O]        relative index of the next entry of the bucket's overflow chain
+//                             (VoxelEntry::offset of the reference layout), 0 = none.
+// mutex     int[numBuckets]   RefExact only: the per-frame try-lock of VoxelUtils.cu:444.
+// heap      uint[N]           free-list of block ids; heapCounter counts down from N-1 (ref :207).
+// blockInfo int4[N]           {x, y, z, slot} of the block that owns heap id i (w = -1: unowned).
+//                             Compaction scans this dense array (16*N_alloc bytes) instead of the
+//                             whole hash table (20*S bytes in the reference).
+// voxels    Voxel[N*512]      reference layout, block = 4 KB contiguous, index z*64+y*8+x.
+// compact16 int4[N]           visible list {x, y, z, ptr} consumed by integrate / raycast splat.
+// compact20 VoxelEntry[N]     the same list in the reference's 20-byte layout (the buffer the
+//                             reference shares with OpenGL, SDFRenderer.cpp:36).
+struct Counters {
+    int heapCounter;              // ref d_heapCounter
+    int compactCount;             // ref d_compactifiedHashCounter[0]
+    int overflowUsed;
+    int dropped;
+    int lastInserted;
+    int icpConverged;             // set when the residual sum is exactly 0 (CameraTracking.cpp:55)
+    unsigned int icpTicket;       // last-CTA-done ticket of the ICP reduction
+    int pad0;
+    unsigned long long numUpdated;
+};
+
+struct FrameParams {
+    float pose[16];   // camera -> world, row-major (HashTableParams::global_transform)
+    float inv[16];    // world -> camera (inv_global_transform), adjugate inverse as SDF_Hashtable.cpp:15
+};
+
+struct IcpState {
+    float delta[16];      // input frame -> target frame, row-major (CameraTracking::deltaTransform)
+    float system[32];     // last reduced vh_icp_system
+    float twist[6];       // Solver::estimate, refreshed lazily by vh_icp_get
+    int iterations;
+    int pad;
+};
+
+struct View {
+    int4* entries;
+    int* chain;
+    int* mutex;
+    unsigned int* heap;
+    int4* blockInfo;
+    Voxel* voxels;
+    int4* compact16;
+    VoxelEntry* compact20;
+    Counters* ctr;
+    const FrameParams* frame;
+
+    unsigned int numBuckets, bucketSize, chainMax, numVoxelBlocks, numSlots, overflowSlots;
+    float voxelSize, invVoxelSize, truncation, truncScale, wMax, wSample;
+    float depthMin, depthMax, invDepthRange, depthScale;
+    int W, H;
+    float fx, fy, cx, cy;
+    float K[9], Kinv[9];                 // tracking-side intrinsics (SetCameraIntrinsic)
+    float wr, hb, nl, nr, nt, nb, rad;   // Fixed frustum constants (DESIGN.md "visibility")
+    int partCount, partRank;
+    float icpDistThres, icpNormalThres;
+};
+
+constexpr int kIcpMaxBlocks = 1024;
+
+struct Pose16f { float m[16]; };
+
+}  // namespace vh
+
+struct vh_context {
+    vh_config cfg;
+    int device;
+    vh::View v;
+    vh::FrameParams* frame;
+    vh::IcpState* icp;
+    float* icpPartials;       // kIcpMaxBlocks x 32
+    int numSMs;
+    size_t bytesAllocated;
+    // host-visible copy of the RefExact fusion-side projection flag etc.
+    bool intrinsicsSet;
+};
+
+namespace vh {
+
+// launchers (each is stream-ordered, no sync). policy dispatch happens inside.
+cudaError_t launch_reset(vh_context* c, cudaStream_t s);
+cudaError_t launch_set_frame_host(vh_context* c, const float* pose16, cudaStream_t s);
+cudaError_t launch_set_frame_device(vh_context* c, const float* d_pose, const float* d_delta, float* d_poseOut, cudaStream_t s);
+cudaError_t launch_alloc(vh_context* c, const float4* verts, cudaStream_t s);
+cudaError_t launch_reset_mutex(vh_context* c, cudaStream_t s);
+cudaError_t launch_compact(vh_context* c, cudaStream_t s);
+cudaError_t launch_integrate(vh_context* c, const float4* verts, const float* depthf, int countOverride, cudaStream_t s);
+cudaError_t launch_preprocess(vh_context* c, const uint16_t* depth, float4* verts, float4* normals, float* depthf, cudaStream_t s);
+cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
+                            int row0, int row1, vh_icp_system* d_out, bool solve, cudaStream_t s);
+cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
+                               int row0, int row1, vh_icp_system* d_out, bool solve, bool first, cudaStream_t s);
+cudaError_t launch_icp_solve(vh_context* c, const vh_icp_system* d_sys, cudaStream_t s);
+cudaError_t launch_icp_reset(vh_context* c, bool resetDelta, cudaStream_t s);
+cudaError_t launch_icp_set_twist(vh_context* c, const float* twist6, cudaStream_t s);
+cudaError_t launch_icp_twist(vh_context* c, cudaStream_t s);
+cudaError_t launch_find_corr(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
+                             const float* delta16_host, float4* corr, float4* corrN, float* res, float* d_err, cudaStream_t s);
+cudaError_t launch_jacobians(vh_context* c, const float4* corr, const float4* corrN, float* J, cudaStream_t s);
+cudaError_t launch_reduce_corr(vh_context* c, const float4* corr, const float4* corrN, const float* res,
+                               vh_icp_system* d_out, cudaStream_t s);
+cudaError_t launch_linear_system_300(vh_context* c, const float4* in, const float4* corr, const float4* corrN,
+                                     float* d_out, cudaStream_t s);
+cudaError_t launch_raycast(vh_context* c, float4* verts, float4* normals, cudaStream_t s);
+cudaError_t launch_export_entries(vh_context* c, VoxelEntry* d_out, int* d_count, cudaStream_t s);
+
+}  // namespace vh
+
+#endif

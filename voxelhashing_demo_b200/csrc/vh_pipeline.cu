@@ -1,0 +1,209 @@
+// vh_pipeline.cu -- native per-frame runtime: the reference's host loop
+// (Application.cpp:73-84: preProcess -> Align -> getTransform -> integrate) as ONE stream-ordered
+// sequence with no host synchronisation, captured into CUDA graphs.
+//
+// Per frame:   [H2D depth] -> preprocess -> { ICP x iterations -> pose <- pose * delta -> alloc ->
+//              compact -> integrate [-> raycast] } -> [D2H pose]
+// The braces are a CUDA graph (one per buffer parity in frame-to-frame mode, where the previous
+// frame's maps are the ICP target).  The pose lives in device memory and is chained on the device,
+// so frame k+1 can be enqueued before frame k has finished.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "vh_internal.h"
+
+using namespace vh;
+
+struct vh_pipeline {
+    vh_context* ctx;
+    int iterations;
+    int mode;
+    bool useGraph;
+    long long frame;
+    long long launches;
+    float* d_pose;                 // camera -> world of the latest frame, row-major
+    uint16_t* d_depthStage;        // H2D landing buffer of push_host
+    float4* verts[2];
+    float4* normals[2];
+    float* depthf[2];
+    float4* modelVerts;            // raycast maps (frame-to-model)
+    float4* modelNormals;
+    cudaGraph_t graph[2];
+    cudaGraphExec_t exec[2];
+    bool haveGraph[2];
+};
+
+namespace {
+thread_local std::string g_pipeError;
+int pfail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    g_pipeError = what;
+    if (e != cudaSuccess) { g_pipeError += ": "; g_pipeError += cudaGetErrorString(e); }
+    fprintf(stderr, "vh_pipeline: %s\n", g_pipeError.c_str());
+    return code;
+}
+#define PCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return pfail(VH_ERR_CUDA, #expr, _e); } while (0)
+
+// the tracked part of a frame (everything after preprocess); returns kernels launched via *n
+cudaError_t enqueueBody(vh_pipeline* p, int par, bool track, cudaStream_t s, int* n) {
+    vh_context* c = p->ctx;
+    cudaError_t e;
+    int k = 0;
+    const float4* in = p->verts[par];
+    const float4* inN = p->normals[par];
+    if (track) {
+        const float4* tg = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelVerts : p->verts[1 - par];
+        const float4* tgN = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelNormals : p->normals[1 - par];
+        for (int it = 0; it < p->iterations; ++it) {                       // CameraTracking.cpp:35
+            e = launch_icp_iter_ex(c, in, inN, tg, tgN, 0, c->v.H, nullptr, true, it == 0, s);
+            if (e != cudaSuccess) return e;
+            ++k;
+        }
+        e = launch_set_frame_device(c, p->d_pose, c->icp->delta, p->d_pose, s);   // T_k = T_{k-1} * delta
+    } else {
+        e = launch_set_frame_device(c, p->d_pose, nullptr, nullptr, s);
+    }
+    if (e != cudaSuccess) return e;
+    ++k;
+    if (c->cfg.policy == VH_POLICY_REF_EXACT) { e = launch_reset_mutex(c, s); if (e != cudaSuccess) return e; ++k; }
+    e = launch_alloc(c, in, s);                                            // SDF_Hashtable.cpp:27
+    if (e != cudaSuccess) return e;
+    e = launch_compact(c, s);                                              // :30
+    if (e != cudaSuccess) return e;
+    e = launch_integrate(c, in, c->cfg.policy == VH_POLICY_FIXED ? p->depthf[par] : nullptr, -1, s);   // :36
+    if (e != cudaSuccess) return e;
+    k += 3;
+    if (p->mode == VH_TRACK_FRAME_TO_MODEL) {
+        e = launch_raycast(c, p->modelVerts, p->modelNormals, s);
+        if (e != cudaSuccess) return e;
+        ++k;
+    }
+    *n = k;
+    return cudaSuccess;
+}
+}  // namespace
+
+extern "C" {
+
+int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGraph, vh_pipeline** out) {
+    if (!ctx || !out) return pfail(VH_ERR_INVALID, "vh_pipeline_create: null argument");
+    if (mode == VH_TRACK_FRAME_TO_MODEL && ctx->cfg.policy != VH_POLICY_FIXED)
+        return pfail(VH_ERR_INVALID, "vh_pipeline_create: frame-to-model tracking needs the Fixed policy");
+    vh_pipeline* p = new vh_pipeline();
+    memset(static_cast<void*>(p), 0, sizeof(*p));
+    p->ctx = ctx;
+    p->iterations = icpIterations > 0 ? icpIterations : ctx->cfg.icpIterations;
+    p->mode = mode;
+    p->useGraph = useGraph != 0;
+    const size_t px = (size_t)ctx->v.W * ctx->v.H;
+    cudaError_t e = cudaSuccess;
+    auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    chk(cudaMalloc((void**)&p->d_pose, 16 * sizeof(float)));
+    chk(cudaMalloc((void**)&p->d_depthStage, px * sizeof(uint16_t)));
+    for (int i = 0; i < 2; ++i) {
+        chk(cudaMalloc((void**)&p->verts[i], px * sizeof(float4)));
+        chk(cudaMalloc((void**)&p->normals[i], px * sizeof(float4)));
+        chk(cudaMalloc((void**)&p->depthf[i], px * sizeof(float)));
+    }
+    if (mode == VH_TRACK_FRAME_TO_MODEL) {
+        chk(cudaMalloc((void**)&p->modelVerts, px * sizeof(float4)));
+        chk(cudaMalloc((void**)&p->modelNormals, px * sizeof(float4)));
+    }
+    if (e != cudaSuccess) { vh_pipeline_destroy(p); return pfail(VH_ERR_CUDA, "vh_pipeline_create: cudaMalloc", e); }
+    const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    cudaMemcpy(p->d_pose, ident, sizeof(ident), cudaMemcpyHostToDevice);
+    *out = p;
+    return VH_OK;
+}
+
+void vh_pipeline_destroy(vh_pipeline* p) {
+    if (!p) return;
+    for (int i = 0; i < 2; ++i) {
+        if (p->haveGraph[i]) { cudaGraphExecDestroy(p->exec[i]); cudaGraphDestroy(p->graph[i]); }
+        cudaFree(p->verts[i]); cudaFree(p->normals[i]); cudaFree(p->depthf[i]);
+    }
+    cudaFree(p->modelVerts); cudaFree(p->modelNormals); cudaFree(p->d_pose); cudaFree(p->d_depthStage);
+    delete p;
+}
+
+// New sequence: frame counter and pose; the table itself is reset with vh_reset.
+int vh_pipeline_reset(vh_pipeline* p, const float* pose16_host, vh_stream s) {
+    if (!p) return pfail(VH_ERR_INVALID, "vh_pipeline_reset: null pipeline");
+    const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+    PCUDA(cudaStreamSynchronize(st));
+    PCUDA(cudaMemcpy(p->d_pose, pose16_host ? pose16_host : ident, 16 * sizeof(float), cudaMemcpyHostToDevice));
+    PCUDA(launch_icp_reset(p->ctx, true, st));
+    p->frame = 0;
+    return VH_OK;
+}
+
+int vh_pipeline_push_device(vh_pipeline* p, const uint16_t* d_depth, vh_stream s) {
+    if (!p || !d_depth) return pfail(VH_ERR_INVALID, "vh_pipeline_push_device: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+    vh_context* c = p->ctx;
+    const int par = (int)(p->frame & 1);
+    PCUDA(launch_preprocess(c, d_depth, p->verts[par], p->normals[par], p->depthf[par], st));   // Application.cpp:73
+    p->launches += 1;
+    const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
+    int n = 0;
+    const int slot = p->mode == VH_TRACK_FRAME_TO_MODEL ? 0 : par;
+    if (track && p->useGraph && st != nullptr) {
+        // frame-to-model always reads maps[par] too, so keep one graph per parity in both modes
+        if (!p->haveGraph[par]) {
+            PCUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            cudaError_t e = enqueueBody(p, par, true, st, &n);
+            cudaGraph_t g = nullptr;
+            cudaError_t e2 = cudaStreamEndCapture(st, &g);
+            if (e != cudaSuccess) return pfail(VH_ERR_CUDA, "pipeline capture", e);
+            if (e2 != cudaSuccess) return pfail(VH_ERR_CUDA, "cudaStreamEndCapture", e2);
+            p->graph[par] = g;
+            PCUDA(cudaGraphInstantiate(&p->exec[par], g, 0));
+            p->haveGraph[par] = true;
+        } else {
+            n = p->iterations + 4 + (p->mode == VH_TRACK_FRAME_TO_MODEL ? 1 : 0) + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
+        }
+        PCUDA(cudaGraphLaunch(p->exec[par], st));
+    } else {
+        PCUDA(enqueueBody(p, par, track, st, &n));
+    }
+    (void)slot;
+    p->launches += n;
+    p->frame += 1;
+    return VH_OK;
+}
+
+// e2e entry: depth in (pinned) host memory, pose back to host memory; returns after enqueueing.
+int vh_pipeline_push_host(vh_pipeline* p, const uint16_t* h_depth, float* h_pose_out16, vh_stream s) {
+    if (!p || !h_depth) return pfail(VH_ERR_INVALID, "vh_pipeline_push_host: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+    const size_t bytes = (size_t)p->ctx->v.W * p->ctx->v.H * sizeof(uint16_t);
+    PCUDA(cudaMemcpyAsync(p->d_depthStage, h_depth, bytes, cudaMemcpyHostToDevice, st));
+    int rc = vh_pipeline_push_device(p, p->d_depthStage, s);
+    if (rc != VH_OK) return rc;
+    if (h_pose_out16) PCUDA(cudaMemcpyAsync(h_pose_out16, p->d_pose, 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return VH_OK;
+}
+
+int vh_pipeline_pose(vh_pipeline* p, float* pose16, vh_stream s) {
+    if (!p || !pose16) return pfail(VH_ERR_INVALID, "vh_pipeline_pose: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+    PCUDA(cudaMemcpyAsync(pose16, p->d_pose, 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PCUDA(cudaStreamSynchronize(st));
+    return VH_OK;
+}
+
+const float* vh_pipeline_pose_device(vh_pipeline* p) { return p ? p->d_pose : nullptr; }
+
+// which: 0 = maps of the latest pushed frame, 1 = ICP target of the NEXT frame's tracking
+int vh_pipeline_maps(vh_pipeline* p, int which, float4** verts, float4** normals) {
+    if (!p || !verts || !normals || p->frame == 0) return pfail(VH_ERR_INVALID, "vh_pipeline_maps: bad argument / no frame yet");
+    const int last = (int)((p->frame - 1) & 1);
+    if (which == 1 && p->mode == VH_TRACK_FRAME_TO_MODEL) { *verts = p->modelVerts; *normals = p->modelNormals; }
+    else { *verts = p->verts[last]; *normals = p->normals[last]; }
+    return VH_OK;
+}
+
+long long vh_pipeline_launches(vh_pipeline* p) { return p ? p->launches : 0; }
+
+}  // extern "C"
