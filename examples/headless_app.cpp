@@ -1,0 +1,58 @@
+// examples/headless_app.cpp -- the reference's host loop (Application.cpp:24-103), headless.
+// Same objects, same call order: CameraTracking + SDF_Hashtable, preProcess on two depth frames,
+// Align, getTransform, integrate.  Inputs are two synthetic frames (plane z = 2.5 m + sphere) instead
+// of assets/T0.png / T1.png, which the reference does not ship.
+//   usage: vh_headless_app [dump.txt]
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "CameraTracking.h"
+#include "SDF_Hashtable.h"
+
+extern "C" void preProcess(float4* positions, float4* normals, const uint16_t* depth);   // Application.cpp:22
+
+static std::vector<uint16_t> renderFrame(float camX) {
+    const float fx = 517.3f, fy = 516.5f, cx = 318.6f, cy = 255.3f;
+    std::vector<uint16_t> d(640 * 480);
+    for (int v = 0; v < 480; ++v)
+        for (int u = 0; u < 640; ++u) {
+            double dx = (u - cx) / fx, dy = (v - cy) / fy, best = 2.5;   // plane z = 2.5
+            double ox = camX, oz = -2.0;                                 // sphere centre (0,0,2) r 0.5, camera at (camX,0,0)
+            double a = dx * dx + dy * dy + 1.0, b = 2.0 * (dx * ox + oz), c = ox * ox + oz * oz - 0.25, disc = b * b - 4 * a * c;
+            if (disc >= 0) { double s = (-b - std::sqrt(disc)) / (2 * a); if (s > 0 && s < best) best = s; }
+            d[v * 640 + u] = (uint16_t)std::lround(best * 5000.0);
+        }
+    return d;
+}
+
+int main(int argc, char** argv) {
+    const size_t px = 640 * 480;
+    CameraTracking tracker(640, 480);                    // Application.cpp:32
+    SDF_Hashtable fusionModule;                          // :33
+    std::vector<uint16_t> img1 = renderFrame(0.0f), img2 = renderFrame(0.01f);
+    uint16_t *d_depthInput, *d_depthTarget;
+    float4 *d_input, *d_inputNormals, *d_target, *d_targetNormals;
+    cudaMalloc(&d_depthInput, px * 2); cudaMalloc(&d_depthTarget, px * 2);
+    cudaMalloc(&d_input, px * 16); cudaMalloc(&d_inputNormals, px * 16);
+    cudaMalloc(&d_target, px * 16); cudaMalloc(&d_targetNormals, px * 16);
+    cudaMemcpy(d_depthInput, img1.data(), px * 2, cudaMemcpyHostToDevice);      // :40-43
+    cudaMemcpy(d_depthTarget, img2.data(), px * 2, cudaMemcpyHostToDevice);
+    preProcess(d_input, d_inputNormals, d_depthInput);                          // :73
+    preProcess(d_target, d_targetNormals, d_depthTarget);                       // :74
+    tracker.Align(d_input, d_inputNormals, d_target, d_targetNormals, d_depthInput, d_depthTarget);   // :75 (commented out there)
+    Matrix4x4f T = tracker.getTransform();                                      // :76
+    std::printf("Final rigid transform (input -> target):\n");
+    for (int r = 0; r < 4; ++r) std::printf("  % .6f % .6f % .6f % .6f\n", T(r, 0), T(r, 1), T(r, 2), T(r, 3));
+    float4x4 identity;
+    identity.setIdentity();
+    fusionModule.integrate(identity, d_input, d_inputNormals);                  // :82-84
+    std::printf("occupiedBlockCount : %d\n", fusionModule.occupiedBlockCount());   // SDF_Hashtable.cpp:31
+    if (argc > 1 && vh_dump_text(fusionModule.context(), argv[1]) != VH_OK) return 1;   // :85 printSDFdata
+    bool ok = std::fabs(T(0, 3) - 0.01f) < 5e-3f && fusionModule.occupiedBlockCount() == 199;
+    std::printf("%s\n", ok ? "OK" : "MISMATCH");
+    return ok ? 0 : 2;
+}

@@ -2,7 +2,7 @@
 what they produce.  One process per table geometry: the reference keeps its table in process-global
 __constant__/host state (VoxelUtils.cu:23-26), so it can be initialised only once.
 
-usage: ref_pin_worker.py OUT.npz NUM_BUCKETS FRAME_K[,FRAME_K...] [align]
+usage: ref_pin_worker.py OUT.npz NUM_BUCKETS FRAME_K[,FRAME_K...] [align] [single]
 """
 import ctypes as C
 import os
@@ -17,7 +17,8 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     out, nb, ks = sys.argv[1], int(sys.argv[2]), [int(k) for k in sys.argv[3].split(",")]
-    do_align = len(sys.argv) > 4 and sys.argv[4] == "align"
+    do_align = "align" in sys.argv[4:]
+    passes = 1 if "single" in sys.argv[4:] else 4
     import torch
 
     from oracle import binding as ob
@@ -40,13 +41,21 @@ def main():
         maps = []
         for i, k in enumerate(ks):
             pose = scenes.trajectory_C2(k).astype(np.float32)
-            depth = scenes.render_depth(scenes.scene_S1(), pose, 640, 480, cfg.fx, cfg.fy, cfg.cx, cfg.cy)
+            depth = scenes.render_depth((scenes.scene_S1T() if do_align else scenes.scene_S1()), pose, 640, 480, cfg.fx, cfg.fy, cfg.cx, cfg.cy)
             d = torch.from_numpy(depth.reshape(-1).copy()).cuda()
             v = torch.zeros((n, 4), device="cuda")
             nm = torch.zeros((n, 4), device="cuda")
             ref.ref_preprocess(v.data_ptr(), nm.data_ptr(), d.data_ptr())
             p = np.ascontiguousarray(pose.reshape(16))
-            occ = ref.ref_integrate(p.ctypes.data, v.data_ptr(), nm.data_ptr())
+            if passes == 1:
+                occ = ref.ref_integrate(p.ctypes.data, v.data_ptr(), nm.data_ptr())     # SDF_Hashtable::integrate as is
+            else:
+                # allocation to convergence (one insert per bucket per pass, quirk Q4), then compact + integrate
+                for _ in range(passes):
+                    ref.ref_stage_begin(p.ctypes.data)
+                    ref.ref_stage_alloc(v.data_ptr(), nm.data_ptr())
+                occ = ref.ref_stage_compact()
+                ref.ref_stage_integrate(v.data_ptr())
             torch.cuda.synchronize()
             maps.append((v, nm))
             slots = ref.ref_num_slots()

@@ -1,0 +1,102 @@
+"""CPU suite: the C-ABI library builds for sm_100a, loads, exports every symbol include/vh/abi.h
+declares, agrees with the reference's struct layouts, and refuses to run without a GPU (no fallback)."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from voxelhashing_demo_b200 import Config, Context, VHError
+from voxelhashing_demo_b200 import lib as L
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    lib = L.load_library()
+    header = (ROOT / "include" / "vh" / "abi.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", header))
+    declared -= {"VH_REF", "defined", "sizeof"}
+    declared = {d for d in declared if not d.isupper()}
+    assert declared, "no prototypes parsed"
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, f"declared in abi.h but not exported: {missing}"
+    # and the python-side lists cover the header
+    assert declared <= set(L.LEGACY_SYMBOLS) | set(L.HANDLE_SYMBOLS)
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(L.LIB_PATH)], capture_output=True, text=True).stdout
+    for name in L.LEGACY_SYMBOLS:                                  # unmangled: C linkage, as the reference's callers bind them
+        assert re.search(rf"\sT {name}$", nm, flags=re.M), name
+    # the C++ host classes are exported too (mangled)
+    for cls in ("SDF_Hashtable", "CameraTracking", "Solver"):
+        assert re.search(rf"\sT _ZN\d+{cls}", nm), cls
+
+
+def test_struct_layouts_match_reference():
+    """SURVEY.md Appendix A.1 (measured from the reference headers with nvcc 12.9 / gcc 13.3)."""
+    assert C.sizeof(L.HashTableParams) == 176
+    off = {n: getattr(L.HashTableParams, n).offset for n, _ in L.HashTableParams._fields_}
+    assert (off["numBuckets"], off["voxelBlockSize"], off["truncation"], off["integrationWeightMax"]) == (128, 144, 164, 172)
+    assert L.VOXEL_ENTRY_DTYPE.itemsize == 20 and L.VOXEL_ENTRY_DTYPE.fields["ptr"][1] == 12 and L.VOXEL_ENTRY_DTYPE.fields["offset"][1] == 16
+    assert L.VOXEL_DTYPE.itemsize == 8 and C.sizeof(L.VhIcpSystem) == 128
+
+
+def test_header_compiles_as_c_and_cxx(tmp_path):
+    """abi.h is a C header (plain pointers and sizes) and a C++ header; static_asserts pin the layouts."""
+    (tmp_path / "c.c").write_text('#include "vh/abi.h"\nint main(void){ vh_config c; vh_default_config(&c); return (int)sizeof(HashTableParams) - 176; }\n')
+    (tmp_path / "cc.cpp").write_text(
+        '#include "SDF_Hashtable.h"\n#include "CameraTracking.h"\n'
+        "static_assert(sizeof(float4x4) == 64, \"\");\n"
+        "int main(){ float4x4 m; m.setIdentity(); float4x4 i = m.getInverse(); return i.m11 == 1.0f ? 0 : 1; }\n")
+    inc = ["-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include"]
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-fsyntax-only", *inc, str(tmp_path / "c.c")], check=True)
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", *inc, str(tmp_path / "cc.cpp")], check=True)
+
+
+def test_default_config_is_the_reference_defaults(built_library):
+    lib = L.load_library()
+    c = L.VhConfig()
+    lib.vh_default_config(C.byref(c))
+    t = c.table                                                      # common.h:39-50
+    assert (t.numBuckets, t.bucketSize, t.attachedLinkedListSize, t.numVoxelBlocks, t.voxelBlockSize) == (5000, 5, 4, 1000, 8)
+    assert (t.voxelSize, t.truncation, t.truncScale, t.integrationWeightMax) == (np.float32(0.02), 1.0, np.float32(0.01), 255.0)
+    assert (c.width, c.height, c.depthScale, c.icpIterations) == (640, 480, 5000.0, 20)
+    assert np.allclose([c.fx, c.fy, c.cx, c.cy], [517.3, 516.5, 318.6, 255.3]) and c.icpDistThres == np.float32(0.08)
+    assert list(t.global_transform.entries) == list(np.eye(4).reshape(-1))
+
+
+def test_no_gpu_means_loud_failure(built_library):
+    """The product path has no CPU fallback: without a device, creating a context raises."""
+    lib = L.load_library()
+    if lib.vh_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(VHError, match="no CUDA device"):
+        Context(Config())
+    h = C.c_void_p()
+    c = Config().to_c()
+    assert lib.vh_create(C.byref(c), C.byref(h)) == L.VH_ERR_NO_DEVICE and not h
+
+
+def test_product_never_touches_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may reach into oracle/."""
+    pkg = ROOT / "voxelhashing_demo_b200"
+    offenders = []
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")) + \
+            list(pkg.rglob("*.cpp")) + list((ROOT / "include").rglob("*.h")):
+        txt = f.read_text(errors="replace")
+        if re.search(r"vh_oracle|libvh_oracle|from oracle|import oracle|oracle/|libvh_ref", txt):
+            offenders.append(str(f.relative_to(ROOT)))
+    assert not offenders, offenders
+    nm = subprocess.run(["nm", "-D", str(L.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "vo_" not in nm
+
+
+def test_sass_has_the_blackwell_paths(built_library):
+    """The allocation claim is a single 128-bit CAS; integration moves voxels with 128-bit accesses."""
+    sass = subprocess.run(["cuobjdump", "-sass", str(L.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "ATOMG.E.CAS.128" in sass
+    assert "LDG.E.128" in sass and "STG.E.128" in sass
+    assert "MATCH.ANY" in sass and "REDUX" in sass or "MATCH.ANY" in sass

@@ -1,0 +1,341 @@
+"""CPU suite: the oracle against hand-computed values, the reference-derived golden vectors in
+tests/golden/ (captured from the UNMODIFIED reference CUDA kernels on a B200 by
+tests/golden/make_golden.py) and its own invariants."""
+import hashlib
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import entries_to_set, render, rot_err, small_cfg
+
+from voxelhashing_demo_b200 import POLICY_FIXED, Config, scenes
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+# ---- coordinate maps and hash (VoxelUtils.cu:250-326) ---------------------------------------------------
+def test_hash_is_unsigned_modulo(oracle):
+    """Quirk Q7: block (-7, 3, 120), 5000 buckets -> 3034, not the signed-remainder 738."""
+    cfg = Config()
+    assert oracle.hash_block(cfg, -7, 3, 120) == 3034
+    x = np.int64(-7) * 73856093 ^ np.int64(3) * 19349669 ^ np.int64(120) * 83492791
+    assert int(np.uint32(x & 0xFFFFFFFF)) % 5000 == 3034
+    assert oracle.hash_block(cfg, 0, 0, 0) == 0
+    assert oracle.hash_block(cfg, 1, 0, 0) == 73856093 % 5000
+
+
+def test_world2block_rounding_and_floor_division(oracle):
+    cfg = Config()   # voxel 0.02 m, block = 8 voxels = 0.16 m
+    w2b = lambda *p: oracle.world2block(cfg, p)
+    assert w2b(0.0, 0.0, 0.0) == (0, 0, 0)
+    assert w2b(0.149, 0.0, 0.0) == (0, 0, 0)            # voxel 7 (7.45 rounds to 7)
+    assert w2b(0.151, 0.0, 0.0) == (1, 0, 0)            # voxel 8
+    assert w2b(-0.009, 0.0, 0.0) == (0, 0, 0)           # voxel -0.45 -> round half away -> 0  (trunc(-0.45-0.5) = 0)
+    assert w2b(-0.011, 0.0, 0.0) == (-1, 0, 0)          # voxel -1 -> block floor(-1/8) = -1
+    assert w2b(-0.16, -0.17, 2.5) == (-1, -2, 15)       # voxel -8 -> -1; -8.5 -> -9 -> -2; 125 -> 15
+    assert w2b(-0.0, 0.0, 0.0) == (0, 0, 0)             # copysign(1, -0.0) = -1: trunc(-0.0 - 0.5) = 0
+    assert w2b(float("inf"), float("nan"), -float("inf"))[1] == 0   # NaN -> 0 on the device
+    assert w2b(float("inf"), 0, 0)[0] == (2**31 - 1) // 8            # saturating conversion
+
+
+def test_block_in_frustum_quirks(oracle):
+    """Q1/Q2: min corner, camera->world transform, transposed K; block (0,0,0) gives 0/0 = NaN -> pixel 0 -> inside."""
+    cfg = Config()
+    I = np.eye(4, dtype=np.float32)
+    assert oracle.block_in_frustum(cfg, I, 0, 0, 0)
+    # with Kt, pixel = (fx x / (cx x + cy y + z), fy y / (...)): a block straight ahead projects near (0, 0)
+    assert oracle.block_in_frustum(cfg, I, 0, 0, 15)
+    assert oracle.block_in_frustum(cfg, I, -1, 0, 15)           # (-82.8, 0, -48.6): both negative -> pixel (1, 0): "inside"
+    assert not oracle.block_in_frustum(cfg, I, 1, -1, 15)       # (82.8, -82.6, 12.5) -> pixel y = -6: outside
+    # a correct pinhole would put (3, 0, 15) at u = 318.6 + 517.3*0.48/2.4 = 422 (inside); the quirk gives 1.6 (inside too)
+    assert oracle.block_in_frustum(cfg, I, 3, 0, 15)
+    fixed = Config(policy=POLICY_FIXED)
+    assert oracle.block_in_frustum(fixed, I, 0, 0, 15) and not oracle.block_in_frustum(fixed, I, 0, 0, -15)
+    assert not oracle.block_in_frustum(fixed, I, 30, 0, 15)     # 4.8 m to the right at 2.4 m depth: outside
+
+
+# ---- SE(3) / linear algebra -----------------------------------------------------------------------------
+def test_se3_exp_log_roundtrip_and_known_values(oracle):
+    rng = np.random.default_rng(7)
+    for _ in range(50):
+        tw = rng.normal(size=6).astype(np.float32) * np.float32(0.3)
+        M = oracle.se3_exp(tw)
+        R = M[:3, :3].astype(np.float64)
+        assert np.allclose(R.T @ R, np.eye(3), atol=1e-6) and abs(np.linalg.det(R) - 1) < 1e-6
+        assert np.allclose(oracle.se3_log(M), tw, atol=2e-6)
+    assert np.allclose(oracle.se3_exp(np.zeros(6)), np.eye(4))
+    M = oracle.se3_exp([1, 2, 3, 0, 0, 0])                        # pure translation
+    assert np.allclose(M[:3, 3], [1, 2, 3]) and np.allclose(M[:3, :3], np.eye(3))
+    M = oracle.se3_exp([0, 0, 0, 0, 0, np.pi / 2])                # rotation about z by 90 deg (twist = (v, omega), SE3.cpp:6-9)
+    assert np.allclose(M[:3, :3], [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-6)
+    tiny = oracle.se3_exp([1e-9, 0, 0, 1e-9, 0, 0])               # series branch
+    assert np.all(np.isfinite(tiny))
+
+
+def test_mat4_inverse_matches_numpy_and_is_exact_for_identity(oracle):
+    assert np.array_equal(oracle.mat4_inverse(np.eye(4)), np.eye(4, dtype=np.float32))
+    T = scenes.trajectory_C2(37).astype(np.float32)
+    assert np.allclose(oracle.mat4_inverse(T), np.linalg.inv(T.astype(np.float64)), atol=1e-6)
+
+
+def test_icp_solve_recovers_known_update(oracle):
+    """x = -(JtJ)^-1 Jtr with a synthetic SPD system; estimate <- log(exp(x) exp(estimate)) (Solver.cpp:109-111)."""
+    rng = np.random.default_rng(3)
+    J = rng.normal(size=(500, 6))
+    x_true = np.array([0.01, -0.02, 0.005, 0.003, -0.004, 0.002])
+    r = -(J @ x_true)
+    A, b = J.T @ J, J.T @ r
+    sysv = np.zeros(32, np.float32)
+    sysv[:21] = A[np.triu_indices(6)]
+    sysv[21:27] = b
+    sysv[27], sysv[28] = 1.0, 500
+    ok, est, delta = oracle.icp_solve(sysv, np.zeros(6, np.float32))
+    assert ok and np.allclose(est, x_true, atol=1e-6)
+    assert np.allclose(delta, oracle.se3_exp(x_true), atol=1e-6)
+    ok2, est2, delta2 = oracle.icp_solve(sysv, est, delta)       # composing the same update again
+    assert ok2 and np.allclose(delta2, oracle.se3_exp(x_true) @ oracle.se3_exp(x_true), atol=1e-6)
+    sing = sysv.copy()
+    sing[:21] = 0
+    assert not oracle.icp_solve(sing, np.zeros(6, np.float32))[0]
+
+
+# ---- pre-processing (CameraTrackingUtils.cu:50-113) -----------------------------------------------------
+def test_preprocess_hand_values(oracle):
+    cfg = small_cfg()
+    depth = np.full((cfg.height, cfg.width), 10000, np.uint16)    # 2.0 m fronto-parallel wall
+    depth[30, 40] = 0
+    v, n, df = oracle.OracleTable(cfg).preprocess(depth)
+    v, n = v.reshape(cfg.height, cfg.width, 4), n.reshape(cfg.height, cfg.width, 4)
+    Kinv = cfg.Kinv()
+    x, y = 100, 50
+    k = (Kinv.reshape(3, 3) @ np.array([x, y, 1], np.float32)).astype(np.float32)
+    assert np.allclose(v[y, x, :3], k * np.float32(2.0), rtol=1e-6) and v[y, x, 3] == 1.0
+    assert np.array_equal(v[30, 40], [0, 0, 0, 1])                 # w = 1 even for depth 0 (quirk Q27)
+    assert np.allclose(n[y, x], [0, 0, -1, 0], atol=1e-6)          # faces the camera
+    assert not n[0].any() and not n[:, 0].any() and not n[-1].any() and not n[:, -1].any()   # borders are zero
+    for yy, xx in ((30, 39), (30, 41), (29, 40), (31, 40), (30, 40)):
+        assert not n[yy, xx].any()                                 # any invalid stencil point -> zero normal
+    assert df[50 * cfg.width + 100] == np.float32(2.0)
+
+
+def test_preprocess_fixed_masks_range_and_discontinuities(oracle):
+    cfg = small_cfg(policy=POLICY_FIXED, depthMax=3.0)
+    depth = np.full((cfg.height, cfg.width), 10000, np.uint16)
+    depth[:, 80:] = 20000                                          # 4 m: beyond depthMax -> masked
+    depth[:, 60:80] = 12000                                        # 2.4 m step: discontinuity at column 60
+    v, n, df = oracle.OracleTable(cfg).preprocess(depth)
+    n = n.reshape(cfg.height, cfg.width, 4)
+    df = df.reshape(cfg.height, cfg.width)
+    assert np.all(df[:, 80:] == 0) and np.all(df[:, :60] == 2.0)
+    assert n[50, 30].any() and not n[50, 59].any() and not n[50, 60].any() and n[50, 70].any()
+
+
+# ---- fusion invariants ------------------------------------------------------------------------------
+def test_c1_reference_probe_numbers(oracle):
+    """SURVEY.md Appendix B numpy probe, reproduced by the C++ oracle: 234 blocks pass the quirk frustum,
+    199 buckets touched, 34 contended, max 3 per bucket; first pass inserts 199."""
+    cfg = Config()
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    ot = oracle.OracleTable(cfg)
+    v, _, _ = ot.preprocess(depth)
+    rep = ot.alloc(np.eye(4), v)
+    assert (rep.requestedBlocks, rep.bucketsTouched, rep.bucketsContended, rep.maxNewPerBucket, rep.inserted) == (234, 199, 34, 3, 199)
+    assert ot.heap_counter() == cfg.numVoxelBlocks - 1 - 199
+    ent = ot.entries()
+    assert sorted(ent[:, 3] // 512) == list(range(cfg.numVoxelBlocks - 199, cfg.numVoxelBlocks))   # ids N-1, N-2, ... (Q6)
+    assert np.all(ent[:, 4] == 0)                                    # offset always 0 (Q5)
+    ins = [rep.inserted]
+    for _ in range(3):
+        ins.append(ot.alloc(np.eye(4), v).inserted)
+    assert ins == [199, 34, 1, 0]
+    nvis = ot.compact(np.eye(4))
+    nupd = ot.integrate(np.eye(4), v)
+    assert nvis == 234 and nupd == 113162
+    blocks = ot.block_dict()
+    w = np.concatenate([b[:, 1] for b in blocks.values()])
+    assert set(np.unique(w)) == {np.float32(0.0), np.float32(0.1)}  # one sample of weight 0.1f (Q12)
+    s = np.concatenate([b[:, 0] for b in blocks.values()])
+    assert s.max() <= 1.0 and s.min() > -1.0                         # truncation 1.0 m, one-sided gate (Q11)
+    ot.integrate(np.eye(4), v)
+    w2 = np.concatenate([b[:, 1] for b in ot.block_dict().values()])
+    assert set(np.unique(w2)) == {np.float32(0.0), np.float32(0.1) + np.float32(0.1)}
+
+
+def test_weight_saturates_at_max(oracle):
+    cfg = small_cfg(integrationWeightMax=0.35)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    ot = oracle.OracleTable(cfg)
+    v, _, _ = ot.preprocess(depth)
+    for _ in range(6):
+        ot.fuse_frame(np.eye(4), v)
+    w = np.concatenate([b[:, 1] for b in ot.block_dict().values()])
+    assert w.max() == np.float32(0.35)
+
+
+def test_heap_exhaustion_leaves_ptr_free(oracle):
+    """Q6: with the heap empty the winner has already written pos; ptr stays -1 and nothing is allocated."""
+    cfg = small_cfg(numVoxelBlocks=10)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    ot = oracle.OracleTable(cfg)
+    v, _, _ = ot.preprocess(depth)
+    rep = ot.alloc(np.eye(4), v)
+    assert rep.inserted == 10 and rep.dropped > 0 and len(ot.entries()) == 10
+
+
+def test_fixed_allocates_truncation_band_and_integrates_metric_tsdf(oracle):
+    cfg = Config(policy=POLICY_FIXED, numBuckets=100003, numVoxelBlocks=8192, truncation=0.06, overflowSlots=1024)
+    pose = scenes.trajectory_C2(25).astype(np.float32)
+    depth = render(cfg, scenes.scene_S1(), pose)
+    ot = oracle.OracleTable(cfg)
+    v, _, df = ot.preprocess(depth)
+    rep, nvis, nupd = ot.fuse_frame(pose, v, df)
+    assert rep.dropped == 0 and rep.inserted == rep.requestedBlocks == nvis > 500
+    assert ot.alloc(pose, v).inserted == 0                          # idempotent
+    # the zero crossing of the fused TSDF lies on the analytic surface: check voxels of the plane z = 2.5
+    blocks = ot.block_dict()
+    errs = []
+    for (bx, by, bz), b in blocks.items():
+        idx = np.arange(512)
+        zc = (bz * 8 + idx // 64) * cfg.voxelSize
+        xc = (bx * 8 + idx % 8) * cfg.voxelSize
+        yc = (by * 8 + (idx // 8) % 8) * cfg.voxelSize
+        far_from_sphere = (xc**2 + yc**2 + (zc - 2.0) ** 2) > 0.75**2
+        sel = (b[:, 1] > 0) & (np.abs(b[:, 0]) < 0.05) & far_from_sphere & (zc > 2.3)
+        # a patch of the wall beside the sphere's shadow (the sphere hides |x|,|y| < ~0.65 of the wall):
+        # the camera-z distance to the wall equals 2.5 - z up to the 1.25 deg tilt of frame 25
+        patch = sel & (xc > 0.75) & (xc < 0.95) & (np.abs(yc) < 0.2)
+        errs.extend(np.abs(b[patch, 0] - (2.5 - zc[patch])))
+    assert len(errs) > 100 and np.max(errs) < 0.001
+
+
+def test_fixed_overflow_chain_and_capacity(oracle):
+    cfg = small_cfg(policy=POLICY_FIXED, numBuckets=16, bucketSize=2, attachedLinkedListSize=3, overflowSlots=4096,
+                    numVoxelBlocks=4096, truncation=0.06)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    ot = oracle.OracleTable(cfg)
+    v, _, df = ot.preprocess(depth)
+    rep, _, _ = ot.fuse_frame(np.eye(4), v, df)
+    ent = ot.entries()
+    assert rep.dropped > 0 and len(ent) <= 16 * (2 + 3)              # bucket + chain capacity
+    assert len(entries_to_set(ent)) == len(ent)
+    per_bucket = {}
+    for e in ent:
+        per_bucket.setdefault(oracle.hash_block(cfg, *e[:3]), []).append(e)
+    assert max(len(b) for b in per_bucket.values()) == 5
+
+
+def test_partition_ranks_are_disjoint_and_cover(oracle):
+    base = dict(policy=POLICY_FIXED, numBuckets=100003, numVoxelBlocks=4096, truncation=0.06, overflowSlots=1024)
+    cfg = small_cfg(**base)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    whole = oracle.OracleTable(cfg)
+    v, _, df = whole.preprocess(depth)
+    whole.fuse_frame(np.eye(4), v, df)
+    union, sizes = {}, []
+    for r in range(4):
+        t = oracle.OracleTable(small_cfg(partCount=4, partRank=r, **base))
+        t.fuse_frame(np.eye(4), v, df)
+        d = t.block_dict()
+        assert not set(d) & set(union)
+        union.update(d)
+        sizes.append(len(d))
+    w = whole.block_dict()
+    assert set(union) == set(w) and all(np.array_equal(bits(union[k]), bits(w[k])) for k in w)
+    assert min(sizes) > 0.15 * len(w)                                 # independent mix balances ownership
+
+
+# ---- ICP -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("policy", [0, POLICY_FIXED])
+def test_icp_align_converges_on_constrained_scene(oracle, policy):
+    cfg = small_cfg(policy=policy, width=320, height=240, fx=517.3 / 2, fy=516.5 / 2, cx=318.6 / 2, cy=255.3 / 2)
+    T0, T1 = scenes.trajectory_C2(0), scenes.trajectory_C2(12)
+    ot = oracle.OracleTable(cfg)
+    tv, tn, _ = ot.preprocess(render(cfg, scenes.scene_S1T(), T0))
+    iv, inn, _ = ot.preprocess(render(cfg, scenes.scene_S1T(), T1))
+    its, est, delta = oracle.icp_align(cfg, iv, inn, tv, tn, 20)
+    truth = np.linalg.inv(T0) @ T1
+    assert its == 20
+    tol_r, tol_t = (1e-3, 2e-3) if policy == POLICY_FIXED else (3e-3, 5e-3)   # RefExact linearises about q, not p (Q23)
+    assert rot_err(delta[:3, :3], truth[:3, :3]) < tol_r and np.max(np.abs(delta[:3, 3] - truth[:3, 3])) < tol_t
+    assert np.allclose(oracle.se3_exp(est), delta, atol=1e-6)
+
+
+def test_correspondence_rules_refexact(oracle):
+    """Q20/Q21: signed distance test, column/row 0 excluded, zero target normal accepted with d = 0."""
+    cfg = small_cfg()
+    depth = np.full((cfg.height, cfg.width), 10000, np.uint16)
+    ot = oracle.OracleTable(cfg)
+    v, n, _ = ot.preprocess(depth)
+    I = np.eye(4, dtype=np.float32)
+    err, corr, corrN, res = oracle.find_correspondences(cfg, v, None, v, n, I)
+    corr = corr.reshape(cfg.height, cfg.width, 4)
+    assert not corr[0].any() and not corr[:, 0].any()                # pixel row 0 / column 0 never match (0 < x)
+    assert corr[60, 80].any() and res.reshape(cfg.height, cfg.width)[60, 80] == 0.0
+    assert corr[cfg.height - 1, 80].any()                            # border target normal is zero: still accepted (d = 0)
+    back = oracle.se3_exp([0, 0, 0.5, 0, 0, 0])                      # source 0.5 m BEHIND the wall: d = -0.5 < 0.08 accepted
+    e2, c2, _, r2 = oracle.find_correspondences(cfg, v, None, v, n, back)
+    assert r2.reshape(cfg.height, cfg.width)[60, 80] == pytest.approx(-0.5, abs=1e-5)
+    front = oracle.se3_exp([0, 0, -0.5, 0, 0, 0])                    # 0.5 m in FRONT: normal is -z, d = +0.5 rejected
+    e3, c3, _, r3 = oracle.find_correspondences(cfg, v, None, v, n, front)
+    assert not c3.reshape(cfg.height, cfg.width, 4)[60, 80].any()
+    J = oracle.jacobians(cfg, corr.reshape(-1, 4), corrN)
+    q, nn = corr[60, 80, :3], np.array([0, 0, -1], np.float32)
+    assert np.allclose(J[60 * cfg.width + 80], np.concatenate([nn, np.cross(q, nn)]), atol=1e-6)
+
+
+# ---- golden vectors captured from the reference's own CUDA kernels ----------------------------------------
+def _golden():
+    f = GOLDEN / "reference_c1.npz"
+    if not f.exists():
+        pytest.skip("tests/golden/reference_c1.npz not captured yet (tests/golden/make_golden.py on the GPU box)")
+    return np.load(f)
+
+
+def test_golden_reference_fusion(oracle):
+    """Outputs of the UNMODIFIED reference kernels on C1 (+ two more frames of a moving camera)."""
+    g = _golden()
+    cfg = Config(numVoxelBlocks=4000)
+    ot = oracle.OracleTable(cfg)
+    ks = [int(k) for k in g["frames"]]
+    for i, k in enumerate(ks):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        depth = render(cfg, scenes.scene_S1(), pose)
+        assert hashlib.sha256(depth.tobytes()).hexdigest() == str(g[f"depth_sha{i}"]), "scene renderer drifted"
+        v, n, _ = ot.preprocess(depth)
+        assert hashlib.sha256(v.tobytes()).hexdigest() == str(g[f"verts_sha{i}"])       # preProcess bit-exact
+        assert hashlib.sha256(n.tobytes()).hexdigest() == str(g[f"normals_sha{i}"])
+        for _ in range(4):
+            ot.alloc(pose, v)
+        nvis = ot.compact(pose)
+        ot.integrate(pose, v)
+        assert nvis == int(g[f"visible{i}"]) and ot.heap_counter() == int(g[f"heap{i}"])
+        assert entries_to_set(ot.entries()) == entries_to_set(g[f"table{i}"])
+        assert entries_to_set(ot.compact_entries()) == entries_to_set(g[f"compact{i}"])
+    for key, blk in zip(g["block_keys"], g["blocks"]):
+        mine = ot.block(*key)
+        assert np.array_equal(bits(mine), bits(blk)), f"block {tuple(key)} differs from the reference"
+
+
+def test_golden_reference_icp(oracle):
+    g = _golden()
+    cfg = Config(numVoxelBlocks=4000)
+    ot = oracle.OracleTable(cfg)
+    tv, tn, _ = ot.preprocess(render(cfg, scenes.scene_S1T(), scenes.trajectory_C2(0)))
+    iv, inn, _ = ot.preprocess(render(cfg, scenes.scene_S1T(), scenes.trajectory_C2(12)))
+    I = np.eye(4, dtype=np.float32)
+    err, corr, corrN, res = oracle.find_correspondences(cfg, iv, None, tv, tn, I)
+    assert hashlib.sha256(res.tobytes()).hexdigest() == str(g["icp_res_sha"])
+    assert hashlib.sha256(corr.tobytes()).hexdigest() == str(g["icp_corr_sha"])
+    assert hashlib.sha256(oracle.jacobians(cfg, corr, corrN).tobytes()).hexdigest() == str(g["icp_jac_sha"])
+    osys = oracle.icp_system(cfg, iv, None, tv, tn, I)
+    scale = float(np.max(np.abs(osys[:21])))
+    assert np.max(np.abs(g["icp_JtJ_upper"] - osys[:21])) <= 1e-5 * scale              # cuBLAS fp32 vs fp64 sums
+    assert np.max(np.abs(g["icp_Jtr"] - osys[21:27])) <= 1e-5 * max(1.0, float(np.max(np.abs(osys[21:27])))) + 1e-8 * scale
+    its, est, delta = oracle.icp_align(cfg, iv, None, tv, tn, 20)
+    assert its == int(g["align_iters"])
+    assert rot_err(delta[:3, :3], g["align_delta"][:3, :3]) <= 1e-4 and np.max(np.abs(delta[:3, 3] - g["align_delta"][:3, 3])) <= 1e-4

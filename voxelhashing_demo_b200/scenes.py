@@ -18,6 +18,7 @@ import numpy as np
 @dataclass
 class Scene:
     planes_z: list = field(default_factory=list)    # world planes z = const
+    planes: list = field(default_factory=list)      # general planes (nx, ny, nz, d): n.p = d
     spheres: list = field(default_factory=list)     # (cx, cy, cz, r)
     boxes: list = field(default_factory=list)       # inward-facing (xmin, xmax, ymin, ymax, zmin, zmax): camera inside
 
@@ -25,6 +26,14 @@ class Scene:
 def scene_S1() -> Scene:
     """Plane z = 2.5 m plus a sphere at (0, 0, 2.0) of radius 0.5 (config C1 / C2)."""
     return Scene(planes_z=[2.5], spheres=[(0.0, 0.0, 2.0, 0.5)])
+
+
+def scene_S1T() -> Scene:
+    """Tracking variant of S1: S1 is rotationally symmetric about the optical axis (rotation about z and
+    in-plane translation are weakly observable), so a floor (y = 1.0), a left wall (x = -1.5) and an
+    off-axis sphere are added; three orthogonal planes constrain all six degrees of freedom (config C2/C5)."""
+    return Scene(planes_z=[2.5], planes=[(0.0, 1.0, 0.0, 1.0), (1.0, 0.0, 0.0, -1.5)],
+                 spheres=[(0.0, 0.0, 2.0, 0.5), (0.9, 0.4, 1.8, 0.3)])
 
 
 def scene_S2() -> Scene:
@@ -86,6 +95,11 @@ def render_depth(scene: Scene, pose: np.ndarray, width: int, height: int, fx: fl
         for zp in scene.planes_z:
             s = (zp - o[2]) / d[..., 2]
             s = np.where(s > 1e-6, s, np.inf)
+            best = np.minimum(best, s)
+        for (nx, ny, nz, dd) in scene.planes:
+            nvec = np.array([nx, ny, nz], dtype=np.float64)
+            s = (dd - float(nvec @ o)) / (d @ nvec)
+            s = np.where(np.isfinite(s) & (s > 1e-6), s, np.inf)
             best = np.minimum(best, s)
         for (sx, sy, sz, r) in scene.spheres:
             oc = o - np.array([sx, sy, sz])
