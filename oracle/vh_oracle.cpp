@@ -669,7 +669,7 @@ void vo_mat4_inverse(const float* m16, float* out16) { mat4_inverse(m16, out16);
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-struct Corr { bool ok; V3 q, n, p; float d; };
+struct Corr { bool ok; V3 q, n, p; float d; float qw, nw; };
 
 // One pixel of FindCorrespondences.  RefExact: :147-182 verbatim in meaning (Q20, Q21).
 inline Corr associate(const vo_config& c, const float* input, const float* inputNormals, const float* target,
@@ -688,7 +688,7 @@ inline Corr associate(const vo_config& c, const float* input, const float* input
         V3 diff{p.x - q[0], p.y - q[1], p.z - q[2]};                            // :168
         float d = diff.x * n[0] + diff.y * n[1] + diff.z * n[2];                // :169
         if (!(d < c.icpDistThres)) return r;                                    // :170 (signed, Q21)
-        r.ok = true; r.q = V3{q[0], q[1], q[2]}; r.n = V3{n[0], n[1], n[2]}; r.p = V3{p.x, p.y, p.z}; r.d = d;
+        r.ok = true; r.q = V3{q[0], q[1], q[2]}; r.n = V3{n[0], n[1], n[2]}; r.p = V3{p.x, p.y, p.z}; r.d = d; r.qw = q[3]; r.nw = n[3];
         return r;
     }
     if (!(s[2] > 0.0f)) return r;
@@ -717,7 +717,7 @@ inline Corr associate(const vo_config& c, const float* input, const float* input
         float cosang = rx * n[0] + ry * n[1] + rz * n[2];
         if (!(cosang > c.icpNormalThres)) return r;
     }
-    r.ok = true; r.q = V3{q[0], q[1], q[2]}; r.n = V3{n[0], n[1], n[2]}; r.p = V3{p.x, p.y, p.z}; r.d = d;
+    r.ok = true; r.q = V3{q[0], q[1], q[2]}; r.n = V3{n[0], n[1], n[2]}; r.p = V3{p.x, p.y, p.z}; r.d = d; r.qw = q[3]; r.nw = n[3];
     return r;
 }
 
@@ -822,8 +822,8 @@ float vo_find_correspondences(const vo_config* cfg, const float* input, const fl
         err += k.d;                                                              // :175 atomicAdd (fp32)
         const int W = cfg->width;
         (void)W;
-        if (corr) { corr[i * 4] = k.q.x; corr[i * 4 + 1] = k.q.y; corr[i * 4 + 2] = k.q.z; corr[i * 4 + 3] = 0; }
-        if (corrNormals) { corrNormals[i * 4] = k.n.x; corrNormals[i * 4 + 1] = k.n.y; corrNormals[i * 4 + 2] = k.n.z; corrNormals[i * 4 + 3] = 0; }
+        if (corr) { corr[i * 4] = k.q.x; corr[i * 4 + 1] = k.q.y; corr[i * 4 + 2] = k.q.z; corr[i * 4 + 3] = k.qw; }   // whole float4, :176
+        if (corrNormals) { corrNormals[i * 4] = k.n.x; corrNormals[i * 4 + 1] = k.n.y; corrNormals[i * 4 + 2] = k.n.z; corrNormals[i * 4 + 3] = k.nw; }
         if (residuals) residuals[i] = k.d;
     }
     return err;

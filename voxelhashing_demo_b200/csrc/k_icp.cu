@@ -15,7 +15,7 @@
 
 namespace vh {
 
-struct Corr { bool ok; float3 q, n, p; float d; };
+struct Corr { bool ok; float3 q, n, p; float d; float qw, nw; };
 
 template <class P>
 __device__ __forceinline__ Corr associate(const View& v, const float* __restrict__ delta, const float4* __restrict__ in,
@@ -36,7 +36,7 @@ __device__ __forceinline__ Corr associate(const View& v, const float* __restrict
         float d = dx * n.x + dy * n.y + dz * n.z;                               // ref :169
         if (!(d < v.icpDistThres)) return r;                                    // ref :170 (signed, Q21)
         r.ok = true; r.q = make_float3(q.x, q.y, q.z); r.n = make_float3(n.x, n.y, n.z);
-        r.p = make_float3(p.x, p.y, p.z); r.d = d;
+        r.p = make_float3(p.x, p.y, p.z); r.d = d; r.qw = q.w; r.nw = n.w;
         return r;
     }
     if (!(s.z > 0.0f)) return r;
@@ -65,7 +65,7 @@ __device__ __forceinline__ Corr associate(const View& v, const float* __restrict
         if (!(cosang > v.icpNormalThres)) return r;
     }
     r.ok = true; r.q = make_float3(q.x, q.y, q.z); r.n = make_float3(n.x, n.y, n.z);
-    r.p = make_float3(p.x, p.y, p.z); r.d = d;
+    r.p = make_float3(p.x, p.y, p.z); r.d = d; r.qw = q.w; r.nw = n.w;
     return r;
 }
 
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) k_find_corr(View v, Pose16f delta, const 
         Corr c = associate<P>(v, sDelta, in, inN, tg, tgN, i);
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f), m = q;
         float r = 0.f;
-        if (c.ok) { q = make_float4(c.q.x, c.q.y, c.q.z, 0.f); m = make_float4(c.n.x, c.n.y, c.n.z, 0.f); r = c.d; e += c.d; }
+        if (c.ok) { q = make_float4(c.q.x, c.q.y, c.q.z, c.qw); m = make_float4(c.n.x, c.n.y, c.n.z, c.nw); r = c.d; e += c.d; }   // whole float4s, ref :176-177
         corr[i] = q; corrN[i] = m; res[i] = r;                  // ref :176-178 (+ fills :201-203)
     }
     e = warpSum(e);

@@ -1,0 +1,94 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch).
+
+The hot path shards in exactly two places (BASELINE.json north_star):
+  * fusion  -- the block-coordinate hash space is partitioned, owner(block) = mix(block) mod P; every
+               rank scans the whole frame, inserts / compacts / integrates only the blocks it owns
+               (the ownership test runs inside k_alloc after the warp-level de-duplication), so no
+               voxel ever crosses NVLink.  Exchange: one broadcast of the u16 depth frame per frame.
+  * ICP     -- frame-to-frame ICP needs no model data: image rows are split over the ranks, each rank
+               reduces its 27 (+2) partial sums on the device, ONE all-reduce of 32 floats per
+               iteration, every rank solves the identical 6x6 system (bit-identical pose on all ranks,
+               no second broadcast).
+Everything here is stream-ordered; the only host synchronisation is what NCCL itself needs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def row_range(rank: int, world: int, height: int) -> tuple[int, int]:
+    """Contiguous block of image rows owned by `rank` for the ICP reduction (balanced to +-1 row)."""
+    base, rem = divmod(height, world)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)
+
+
+def owner_of(x: int, y: int, z: int, parts: int) -> int:
+    """Host restatement of ownerMix (csrc/vh_device.cuh): which rank owns block (x, y, z)."""
+    m = 0xFFFFFFFF
+    u = ((x * 0x9E3779B1) ^ (y * 0x85EBCA77) ^ (z * 0xC2B2AE3D)) & m
+    u ^= u >> 16
+    u = (u * 0x7FEB352D) & m
+    u ^= u >> 15
+    u = (u * 0x846CA68B) & m
+    u ^= u >> 16
+    return u % parts
+
+
+class PartitionedTracker:
+    """Per-rank driver of one partition: broadcast -> preprocess -> split ICP + all-reduce -> fuse."""
+
+    def __init__(self, ctx, rank: int, world: int, iterations: int | None = None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.iterations = iterations or ctx.cfg.icpIterations
+        cfg = ctx.cfg
+        n = cfg.width * cfg.height
+        self.depth = torch.zeros(n, dtype=torch.uint16, device="cuda") if hasattr(torch, "uint16") else torch.zeros(n, dtype=torch.int16, device="cuda")
+        self.maps = [ctx.new_maps(), ctx.new_maps()]
+        self.sys = torch.zeros(32, dtype=torch.float32, device="cuda")
+        self.d_pose = torch.zeros(16, dtype=torch.float32, device="cuda")
+        self.rows = row_range(rank, world, cfg.height)
+        self.frame = 0
+        self.launches = 0
+
+    def reset(self, pose):
+        self.d_pose.copy_(self.torch.from_numpy(np.ascontiguousarray(pose, dtype=np.float32).reshape(16)))
+        self.ctx.icp_reset(True)
+        self.frame = 0
+
+    def push(self, d_depth=None):
+        """One frame.  Rank 0 passes the device depth image; the others pass None."""
+        ctx, dist = self.ctx, self.dist
+        if self.rank == 0:
+            self.depth.copy_(d_depth.view(self.depth.dtype))
+        if self.world > 1:
+            dist.broadcast(self.depth.view(self.torch.int16), src=0, group=self.group)   # NVLink / NVSwitch
+        par = self.frame & 1
+        v, n, df = self.maps[par]
+        pv, pn, _ = self.maps[1 - par]
+        ctx.preprocess(self.depth, v, n, df)
+        self.launches += 1
+        if self.frame > 0:
+            for _ in range(self.iterations):
+                ctx.icp_reduce(v, n, pv, pn, self.rows[0], self.rows[1], self.sys)
+                if self.world > 1:
+                    dist.all_reduce(self.sys, group=self.group)                           # 32 floats
+                ctx.icp_solve(self.sys)
+                self.launches += 2
+            ctx.pose_compose(self.d_pose, self.d_pose)        # T_k = T_{k-1} * delta, also publishes the frame pose
+        else:
+            ctx.set_pose_device(self.d_pose)
+        self.launches += 1
+        ctx.alloc_blocks(v, n)
+        ctx.compact()
+        ctx.integrate_depthf(df)
+        self.launches += 3
+        self.frame += 1
+
+    def pose(self) -> np.ndarray:
+        self.torch.cuda.synchronize()
+        return self.d_pose.cpu().numpy().reshape(4, 4)
