@@ -439,7 +439,8 @@ def test_legacy_entry_points_match_handle_api(built_library, oracle):
     err = lib.computeCorrespondences(v.data_ptr(), v.data_ptr(), n.data_ptr(), corr.data_ptr(), corrN.data_ptr(), res.data_ptr(),
                                      C.byref(delta), 640, 480)
     oerr, ocorr, ocorrN, ores = oracle.find_correspondences(cfg, ov, None, ov, on, dm)
-    assert np.array_equal(bits(res.cpu().numpy()), bits(ores)) and abs(err - oerr) <= 1e-4 * max(1.0, abs(oerr))
+    assert np.array_equal(bits(res.cpu().numpy()), bits(ores))
+    assert abs(err - float(np.sum(ores.astype(np.float64)))) <= 1e-5 * float(np.sum(np.abs(ores)))   # fp32 sum, any order
     lib.CalculateJacobiansAndResiduals(v.data_ptr(), corr.data_ptr(), corrN.data_ptr(), J.data_ptr())
     torch.cuda.synchronize()
     assert np.array_equal(bits(J.cpu().numpy()), bits(oracle.jacobians(cfg, ocorr, ocorrN)))
