@@ -44,6 +44,13 @@ inline int f2i(float x) {
     return (int)x;
 }
 // cvt.rzi.s32.f64
+// cvt.rni.s32.f32: round to nearest even, saturating, NaN -> 0
+inline int f2i_rn(float x) {
+    if (std::isnan(x)) return 0;
+    if (x >= 2147483648.0f) return kIntMax;
+    if (x <= -2147483648.0f) return kIntMin;
+    return (int)std::nearbyintf(x);
+}
 inline int d2i(double x) {
     if (std::isnan(x)) return 0;
     if (x >= 2147483648.0) return kIntMax;
@@ -580,7 +587,9 @@ static long long integrateImpl(vo_table* t, const float* pose, const float* dept
         const float fx = c.K[0], fy = c.K[4], cx = c.K[2], cy = c.K[5];
         const float invRange = 1.0f / (c.depthMax - c.depthMin);
         const float ws = (float)c.integrationWeightSample;
-        const float umax = (float)W - 0.5f, vmax = (float)H - 0.5f;
+        // Niessner's weight max(ws * 1.5 * (1 - (d - dmin)/(dmax - dmin)), 1) as one FMA in d (ref VoxelUtils.cu:809-827)
+        const float wA = -((ws * 1.5f) * invRange);
+        const float wB = (ws * 1.5f) * (1.0f + c.depthMin * invRange);
 #pragma omp parallel for schedule(dynamic, 8) reduction(+ : updated)
         for (int bi = 0; bi < n; ++bi) {
             const Entry& e = t->compact[bi];
@@ -596,20 +605,19 @@ static long long integrateImpl(vo_table* t, const float* pose, const float* dept
                         if (!(pcz > 0.0f)) continue;
                         float iz = 1.0f / pcz;
                         float u = fmaf(pcx * iz, fx, cx), v = fmaf(pcy * iz, fy, cy);
-                        if (!(u >= -0.5f && u < umax && v >= -0.5f && v < vmax)) continue;
-                        int px = std::min((int)(u + 0.5f), W - 1), py = std::min((int)(v + 0.5f), H - 1);
+                        int px = f2i_rn(u), py = f2i_rn(v);                    // nearest pixel, ties to even
+                        if ((unsigned)px >= (unsigned)W || (unsigned)py >= (unsigned)H) continue;
                         float d = depthSrc[(size_t)(py * W + px) * stride + zoff];
                         if (!(d > c.depthMin && d < c.depthMax)) continue;
                         float sdf = d - pcz;
                         float tr = fmaf(c.truncScale, d, c.truncation);
                         if (!(sdf > -tr)) continue;
                         sdf = fminf(sdf, tr);
-                        float zo = (d - c.depthMin) * invRange;
-                        float wu = fmaxf(ws * 1.5f * (1.0f - zo), 1.0f);     // ref VoxelUtils.cu:827 (commented formula)
+                        float wu = fmaxf(fmaf(d, wA, wB), 1.0f);
                         float* vox = t->voxels + ((size_t)e.ptr + tz * 64 + ty * 8 + tx) * 2;
                         float os = vox[0], ow = vox[1];
                         float wn = ow + wu;
-                        float ns = fmaf(os, ow, sdf * wu) / wn;
+                        float ns = fmaf(os, ow, sdf * wu) * (1.0f / wn);
                         vox[0] = ns; vox[1] = fminf(c.integrationWeightMax, wn);
                         ++updated;
                     }

@@ -339,7 +339,8 @@ def test_golden_reference_icp(oracle):
     assert hashlib.sha256(oracle.jacobians(cfg, corr, corrN).tobytes()).hexdigest() == str(g["icp_jac_sha"])
     osys = oracle.icp_system(cfg, iv, None, tv, tn, I)
     scale = float(np.max(np.abs(osys[:21])))
-    assert np.max(np.abs(g["icp_JtJ_upper"] - osys[:21])) <= 1e-5 * scale              # cuBLAS fp32 vs fp64 sums
+    # cublasSsyrk sums 307200 fp32 products per entry: 8.3e-5 of the scale off the fp64 sum on B200 (Jtr: 1e-7)
+    assert np.max(np.abs(g["icp_JtJ_upper"] - osys[:21])) <= 3e-4 * scale
     assert np.max(np.abs(g["icp_Jtr"] - osys[21:27])) <= 1e-5 * max(1.0, float(np.max(np.abs(osys[21:27])))) + 1e-8 * scale
     its, est, delta = oracle.icp_align(cfg, iv, None, tv, tn, 20)
     assert its == int(g["align_iters"])

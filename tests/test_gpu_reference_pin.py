@@ -131,7 +131,8 @@ def test_reference_icp_pins_oracle_and_cuda(built_library, oracle, tmp_path):
     JtJ = ref["icp_JtJ"].reshape(6, 6)              # column-major, lower triangle valid
     ref_upper = np.array([JtJ[i, j] for i in range(6) for j in range(i, 6)])   # C(j,i) lower == [i*6+j]
     scale = float(np.max(np.abs(osys[:21])))
-    assert np.max(np.abs(ref_upper - osys[:21])) <= 1e-5 * scale
+    # cublasSsyrk accumulates 307200 fp32 products per entry: its own error is ~1e-4 of the scale (measured 8.3e-5 on B200)
+    assert np.max(np.abs(ref_upper - osys[:21])) <= 3e-4 * scale
     assert np.max(np.abs(ref["icp_Jtr"] - osys[21:27])) <= 1e-5 * max(1.0, float(np.max(np.abs(osys[21:27])))) + 1e-8 * scale
     # fused CUDA reduction against the reference's cuBLAS result
     ctx = Context(cfg)
@@ -141,7 +142,8 @@ def test_reference_icp_pins_oracle_and_cuda(built_library, oracle, tmp_path):
     ctx.icp_reduce(g[0], g[1], g[2], g[3], 0, 480, dsys)
     torch.cuda.synchronize()
     gsys = dsys.cpu().numpy()
-    assert np.max(np.abs(gsys[:21] - ref_upper)) <= 1e-5 * scale
+    assert np.max(np.abs(gsys[:21] - ref_upper)) <= 3e-4 * scale               # bound by cuBLAS, see above
+    assert np.max(np.abs(gsys[:21] - osys[:21])) <= 1e-5 * scale               # the fused reduction itself meets 1e-5
     assert np.max(np.abs(gsys[21:27] - ref["icp_Jtr"])) <= 1e-5 * max(1.0, float(np.max(np.abs(ref["icp_Jtr"])))) + 1e-8 * scale
     # Align: pose within 1e-4 of the reference loop
     assert int(ref["align_iters"][0]) == 20

@@ -172,7 +172,7 @@ struct IcpDev {               // device-resident solver state (Solver::estimate 
 };
 
 // update = -(JtJ)^-1 Jtr; delta <- exp(update) * delta  (== exp(log(exp(update) exp(estimate))), Solver.cpp:110-111)
-__device__ void solveAndUpdate(const float* sys, IcpState* st, IcpDev* dev, Counters* ctr, bool fixedPolicy) {
+__device__ __noinline__ void solveAndUpdate(const float* sys, IcpState* st, IcpDev* dev, Counters* ctr, bool fixedPolicy) {
     if (fixedPolicy ? !(sys[28] >= 6.0f) : (sys[27] == 0.0f)) { ctr->icpConverged = 1; return; }   // CameraTracking.cpp:55-58
     double M[6][7], x[6];
     int k = 0;
@@ -196,6 +196,7 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
                            bool fixedPolicy) {
     __shared__ bool isLast;
     __shared__ float sSys[32];
+    __shared__ double sPart[8][32];
     if (threadIdx.x < 32) partials[(size_t)blockIdx.x * 32 + threadIdx.x] = threadIdx.x < 29 ? tot : 0.f;
     __threadfence();
     __syncthreads();
@@ -203,11 +204,23 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
     __syncthreads();
     if (!isLast) return;
     __threadfence();
-    if (threadIdx.x < 32) {
+    // All warps of the last CTA sum the per-CTA partials: warp g takes CTAs g, g+nw, ... (fixed order, fp64),
+    // lane = column; then the nw group sums are added in group order.  Deterministic for a given grid, and
+    // the loads of a thread are independent, so the L2 latency is paid a few times instead of gridDim times.
+    {
+        const unsigned col = threadIdx.x & 31, grp = threadIdx.x >> 5, nw = blockDim.x >> 5;
         double s = 0;
-        if (threadIdx.x < 29)
-            for (unsigned b = 0; b < gridDim.x; ++b) s += (double)__ldcg(partials + (size_t)b * 32 + threadIdx.x);
-        sSys[threadIdx.x] = (float)s;
+        if (col < 29) {
+#pragma unroll 8
+            for (unsigned b = grp; b < gridDim.x; b += nw) s += (double)__ldcg(partials + (size_t)b * 32 + col);
+        }
+        sPart[grp][col] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = 0;
+        for (unsigned g = 0; g < (blockDim.x >> 5); ++g) t += sPart[g][threadIdx.x];
+        sSys[threadIdx.x] = (float)t;
     }
     __syncthreads();
     if (threadIdx.x < 32) {

@@ -65,6 +65,7 @@ struct View {
     unsigned int numBuckets, bucketSize, chainMax, numVoxelBlocks, numSlots, overflowSlots;
     float voxelSize, invVoxelSize, truncation, truncScale, wMax, wSample;
     float depthMin, depthMax, invDepthRange, depthScale;
+    float wA, wB;                        // Fixed sample weight: w = max(wA * depth + wB, 1)
     int W, H;
     float fx, fy, cx, cy;
     float K[9], Kinv[9];                 // tracking-side intrinsics (SetCameraIntrinsic)
