@@ -7,66 +7,93 @@
 // One Gauss-Newton iteration = ONE kernel: projective association, signed point-to-plane
 // residual, the 6-float Jacobian row, 21 + 6 (+2) partial sums kept in registers, warp-shuffle
 // tree, one shared-memory stage per CTA, per-CTA partials to HBM, and the LAST CTA to arrive
-// (ticket) sums the partials in CTA order in fp64 (deterministic), solves the 6x6 system and
-// left-multiplies the SE(3) update into the delta transform -- all on the device, so a 20-iteration
-// Align is 20 back-to-back launches with no host round trip.  The reference moves ~268 B per pixel
-// per iteration through a 7.4 MB Jacobian; this moves the algorithmic 48 B.
+// (ticket) sums the partials in CTA order in fp64 (deterministic), solves the 6x6 system
+// (warp-cooperative Gauss-Jordan) and left-multiplies the SE(3) update into the delta transform --
+// all on the device, so a 20-iteration Align is 20 back-to-back launches with no host round trip.
+// The reference moves ~268 B per pixel per iteration through a 7.4 MB Jacobian; this moves the
+// algorithmic 48 B (64 B when the source normals are checked).
+//
+// r1a profile: at VGA everything is L2-resident and the kernel is LATENCY-bound, not bandwidth-bound
+// (16 warps/SM, two dependent L2 round trips per pixel, one pixel at a time = 1.7 TB/s).  v2 keeps
+// four pixels in flight per thread (4 independent source loads, then up to 12 independent gathers),
+// one 512-thread CTA per SM, and a tail that touches each partial row with one 16-byte load.
 #include "vh_device.cuh"
 
 namespace vh {
 
+constexpr int kIcpThreads = 512;
+
+struct Cand { float3 p; int tidx; };             // transformed source point and target pixel (-1: none)
 struct Corr { bool ok; float3 q, n, p; float d; float qw, nw; };
+
+// First half of FindCorrespondences: transform by delta, project with K (ref :153-162).
+template <class P>
+__device__ __forceinline__ Cand project(const View& v, const float* __restrict__ delta, const float4 s) {
+    Cand c;
+    c.tidx = -1;
+    c.p = make_float3(0.f, 0.f, 0.f);
+    if (!P::fixed) {
+        if (!(s.z != 0)) return c;                                              // ref :153
+        float4 p = mul4(delta, s.x, s.y, s.z, 1.0f);                            // ref :154-155
+        float3 sp = mul3(v.K, p.x, p.y, p.z);                                   // ref :124
+        int ix = d2i((double)(sp.x / sp.z) + 0.5), iy = d2i((double)(sp.y / sp.z) + 0.5);   // ref :128 (Q20)
+        c.p = make_float3(p.x, p.y, p.z);
+        if (!(ix > 0 && iy > 0 && ix < v.W && iy < v.H)) return c;              // ref :162
+        c.tidx = iy * v.W + ix;
+        return c;
+    }
+    if (!(s.z > 0.0f)) return c;
+    float4 p = mul4(delta, s.x, s.y, s.z, 1.0f);
+    if (!(p.z > 0.0f)) return c;
+    float u = (v.fx * p.x + v.cx * p.z) / p.z, w = (v.fy * p.y + v.cy * p.z) / p.z;
+    if (!(u >= -0.5f && u < (float)v.W - 0.5f && w >= -0.5f && w < (float)v.H - 0.5f)) return c;
+    int ix = min((int)(u + 0.5f), v.W - 1), iy = min((int)(w + 0.5f), v.H - 1);
+    c.p = make_float3(p.x, p.y, p.z);
+    c.tidx = iy * v.W + ix;
+    return c;
+}
+
+// Second half: residual and acceptance (ref :166-178).  m = source normal (Fixed, optional).
+template <class P>
+__device__ __forceinline__ Corr accept(const View& v, const float* __restrict__ delta, const Cand& c, const float4 q,
+                                       const float4 n, const float4 m, bool haveM) {
+    Corr r;
+    r.ok = false;
+    const float dx = c.p.x - q.x, dy = c.p.y - q.y, dz = c.p.z - q.z;           // ref :168
+    const float d = dx * n.x + dy * n.y + dz * n.z;                             // ref :169
+    if (!P::fixed) {
+        if (!(d < v.icpDistThres)) return r;                                    // ref :170 (signed, Q21)
+    } else {
+        if (!(q.z > 0.0f)) return r;
+        float nn = n.x * n.x + n.y * n.y + n.z * n.z;
+        if (!(nn > 0.0f)) return r;
+        float e2 = dx * dx + dy * dy + dz * dz;
+        float lim = 3.0f * v.icpDistThres;
+        if (!(e2 < lim * lim)) return r;
+        if (!(fabsf(d) < v.icpDistThres)) return r;
+        if (haveM) {
+            float rx = delta[0] * m.x + delta[1] * m.y + delta[2] * m.z;
+            float ry = delta[4] * m.x + delta[5] * m.y + delta[6] * m.z;
+            float rz = delta[8] * m.x + delta[9] * m.y + delta[10] * m.z;
+            float cosang = rx * n.x + ry * n.y + rz * n.z;
+            if (!(cosang > v.icpNormalThres)) return r;
+        }
+    }
+    r.ok = true; r.q = make_float3(q.x, q.y, q.z); r.n = make_float3(n.x, n.y, n.z);
+    r.p = c.p; r.d = d; r.qw = q.w; r.nw = n.w;
+    return r;
+}
 
 template <class P>
 __device__ __forceinline__ Corr associate(const View& v, const float* __restrict__ delta, const float4* __restrict__ in,
                                           const float4* __restrict__ inN, const float4* __restrict__ tg,
                                           const float4* __restrict__ tgN, int idx) {
-    Corr r;
-    r.ok = false;
-    const float4 s = __ldg(in + idx);
-    if (!P::fixed) {
-        if (!(s.z != 0)) return r;                                              // ref :153
-        float4 p = mul4(delta, s.x, s.y, s.z, 1.0f);                            // ref :154-155
-        float3 sp = mul3(v.K, p.x, p.y, p.z);                                   // ref :124
-        int ix = d2i((double)(sp.x / sp.z) + 0.5), iy = d2i((double)(sp.y / sp.z) + 0.5);   // ref :128 (Q20)
-        if (!(ix > 0 && iy > 0 && ix < v.W && iy < v.H)) return r;              // ref :162
-        const float4 q = __ldg(tg + (size_t)iy * v.W + ix);
-        const float4 n = __ldg(tgN + (size_t)iy * v.W + ix);
-        float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;                   // ref :168
-        float d = dx * n.x + dy * n.y + dz * n.z;                               // ref :169
-        if (!(d < v.icpDistThres)) return r;                                    // ref :170 (signed, Q21)
-        r.ok = true; r.q = make_float3(q.x, q.y, q.z); r.n = make_float3(n.x, n.y, n.z);
-        r.p = make_float3(p.x, p.y, p.z); r.d = d; r.qw = q.w; r.nw = n.w;
-        return r;
-    }
-    if (!(s.z > 0.0f)) return r;
-    float4 p = mul4(delta, s.x, s.y, s.z, 1.0f);
-    if (!(p.z > 0.0f)) return r;
-    float u = (v.fx * p.x + v.cx * p.z) / p.z, w = (v.fy * p.y + v.cy * p.z) / p.z;
-    if (!(u >= -0.5f && u < (float)v.W - 0.5f && w >= -0.5f && w < (float)v.H - 0.5f)) return r;
-    int ix = min((int)(u + 0.5f), v.W - 1), iy = min((int)(w + 0.5f), v.H - 1);
-    const float4 q = __ldg(tg + (size_t)iy * v.W + ix);
-    if (!(q.z > 0.0f)) return r;
-    const float4 n = __ldg(tgN + (size_t)iy * v.W + ix);
-    float nn = n.x * n.x + n.y * n.y + n.z * n.z;
-    if (!(nn > 0.0f)) return r;
-    float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
-    float e2 = dx * dx + dy * dy + dz * dz;
-    float lim = 3.0f * v.icpDistThres;
-    if (!(e2 < lim * lim)) return r;
-    float d = dx * n.x + dy * n.y + dz * n.z;
-    if (!(fabsf(d) < v.icpDistThres)) return r;
-    if (inN != nullptr && v.icpNormalThres > -1.0f) {
-        const float4 m = __ldg(inN + idx);
-        float rx = delta[0] * m.x + delta[1] * m.y + delta[2] * m.z;
-        float ry = delta[4] * m.x + delta[5] * m.y + delta[6] * m.z;
-        float rz = delta[8] * m.x + delta[9] * m.y + delta[10] * m.z;
-        float cosang = rx * n.x + ry * n.y + rz * n.z;
-        if (!(cosang > v.icpNormalThres)) return r;
-    }
-    r.ok = true; r.q = make_float3(q.x, q.y, q.z); r.n = make_float3(n.x, n.y, n.z);
-    r.p = make_float3(p.x, p.y, p.z); r.d = d; r.qw = q.w; r.nw = n.w;
-    return r;
+    Cand c = project<P>(v, delta, __ldg(in + idx));
+    if (c.tidx < 0) { Corr r; r.ok = false; return r; }
+    const bool haveM = P::fixed && inN != nullptr && v.icpNormalThres > -1.0f;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (haveM) m = __ldg(inN + idx);
+    return accept<P>(v, delta, c, __ldg(tg + c.tidx), __ldg(tgN + c.tidx), m, haveM);
 }
 
 // 29 running sums: 21 upper-triangle JtJ (row by row), 6 Jtr, residual sum, count.
@@ -81,6 +108,13 @@ __device__ __forceinline__ void accumulate(float* acc, const float* J, float r) 
     for (int i = 0; i < 6; ++i) acc[21 + i] += J[i] * r;
     acc[27] += r;
     acc[28] += 1.0f;
+}
+
+template <class P>
+__device__ __forceinline__ void accumulateCorr(float* acc, const Corr& c) {
+    const float3 a = P::fixed ? c.p : c.q;                 // ref Solver.cu:26 uses the TARGET point (Q23)
+    float J[6] = {c.n.x, c.n.y, c.n.z, a.y * c.n.z - a.z * c.n.y, a.z * c.n.x - a.x * c.n.z, a.x * c.n.y - a.y * c.n.x};
+    accumulate(acc, J, c.d);
 }
 
 // CTA reduction of 29 sums; result valid in warp 0 lane k (k < 29) as the return value.
@@ -101,29 +135,28 @@ __device__ __forceinline__ float blockReduce29(float* acc, float (*sm)[32]) {
 }
 
 // ---- SE(3) pieces, fp64, closed form (Eigen's matrix exp/log are not available) ----
-__device__ void soTerms(const double* w, double& A, double& B, double& C) {
+__device__ __forceinline__ void soTerms(const double* w, double& A, double& B, double& C) {
     double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
     double th = sqrt(t2);
     if (th < 1e-6) { A = 1.0 - t2 / 6.0; B = 0.5 - t2 / 24.0; C = 1.0 / 6.0 - t2 / 120.0; }
     else { double s, c; sincos(th, &s, &c); A = s / th; B = (1.0 - c) / t2; C = (th - s) / (t2 * th); }
 }
-__device__ void se3Exp(const double* tw, double* M) {          // ref SE3Exp, twist = (v, omega)
+// element (i, j) of exp([[w]x v; 0 0]) (ref SE3Exp, twist = (v, omega))
+__device__ __forceinline__ double se3ExpElement(const double* tw, double A, double B, double C, int i, int j) {
     const double* vv = tw; const double* w = tw + 3;
+    if (i == 3) return j == 3 ? 1.0 : 0.0;
+    const double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double K2row[3];
+    for (int c = 0; c < 3; ++c) K2row[c] = K[i * 3] * K[c] + K[i * 3 + 1] * K[3 + c] + K[i * 3 + 2] * K[6 + c];
+    if (j < 3) return ((i == j) ? 1.0 : 0.0) + A * K[i * 3 + j] + B * K2row[j];
+    double t = 0;
+    for (int c = 0; c < 3; ++c) t += (((i == c) ? 1.0 : 0.0) + B * K[i * 3 + c] + C * K2row[c]) * vv[c];
+    return t;
+}
+__device__ void se3Exp(const double* tw, double* M) {
     double A, B, C;
-    soTerms(w, A, B, C);
-    double K[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
-    double K2[9];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) K2[i * 3 + j] = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
-    for (int i = 0; i < 3; ++i) {
-        double t = 0;
-        for (int j = 0; j < 3; ++j) {
-            double I = (i == j) ? 1.0 : 0.0;
-            M[i * 4 + j] = I + A * K[i * 3 + j] + B * K2[i * 3 + j];
-            t += (I + B * K[i * 3 + j] + C * K2[i * 3 + j]) * vv[j];
-        }
-        M[i * 4 + 3] = t;
-    }
-    M[12] = M[13] = M[14] = 0; M[15] = 1;
+    soTerms(tw + 3, A, B, C);
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) M[i * 4 + j] = se3ExpElement(tw, A, B, C, i, j);
 }
 __device__ void se3Log(const double* M, double* tw) {          // ref SE3Log
     double tr = M[0] + M[5] + M[10];
@@ -146,57 +179,78 @@ __device__ void se3Log(const double* M, double* tw) {          // ref SE3Log
     }
     tw[3] = w[0]; tw[4] = w[1]; tw[5] = w[2];
 }
-// x = A^-1 b by Gaussian elimination with partial pivoting (stands in for JTJ.inverse(), Solver.cpp:109)
-__device__ bool solve6(double (*M)[7], double* x) {
-    for (int k = 0; k < 6; ++k) {
-        int p = k;
-        for (int i = k + 1; i < 6; ++i) if (fabs(M[i][k]) > fabs(M[p][k])) p = i;
-        if (!(fabs(M[p][k]) > 1e-300)) return false;
-        if (p != k) for (int j = 0; j < 7; ++j) { double t = M[p][j]; M[p][j] = M[k][j]; M[k][j] = t; }
-        for (int i = k + 1; i < 6; ++i) {
-            double f = M[i][k] / M[k][k];
-            for (int j = k; j < 7; ++j) M[i][j] -= f * M[k][j];
-        }
-    }
-    for (int i = 5; i >= 0; --i) {
-        double s = M[i][6];
-        for (int j = i + 1; j < 6; ++j) s -= M[i][j] * x[j];
-        x[i] = s / M[i][i];
-    }
-    for (int i = 0; i < 6; ++i) if (!isfinite(x[i])) return false;
-    return true;
-}
 
 struct IcpDev {               // device-resident solver state (Solver::estimate / deltaTransform)
     double D[16];             // delta in fp64
 };
-
-// update = -(JtJ)^-1 Jtr; delta <- exp(update) * delta  (== exp(log(exp(update) exp(estimate))), Solver.cpp:110-111)
-__device__ __noinline__ void solveAndUpdate(const float* sys, IcpState* st, IcpDev* dev, Counters* ctr, bool fixedPolicy) {
-    if (fixedPolicy ? !(sys[28] >= 6.0f) : (sys[27] == 0.0f)) { ctr->icpConverged = 1; return; }   // CameraTracking.cpp:55-58
-    double M[6][7], x[6];
-    int k = 0;
-    for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 6; ++j) { M[i][j] = sys[k]; M[j][i] = sys[k]; ++k; }
-    for (int i = 0; i < 6; ++i) M[i][6] = -(double)sys[21 + i];
-    if (!solve6(M, x)) { ctr->icpConverged = 1; return; }
-    double U[16], Pn[16];
-    se3Exp(x, U);
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j)
-            Pn[i * 4 + j] = U[i * 4] * dev->D[j] + U[i * 4 + 1] * dev->D[4 + j] + U[i * 4 + 2] * dev->D[8 + j] + U[i * 4 + 3] * dev->D[12 + j];
-    for (int i = 0; i < 16; ++i) { dev->D[i] = Pn[i]; st->delta[i] = (float)Pn[i]; }
-    st->iterations += 1;
-}
-
 __device__ __forceinline__ IcpDev* devOf(IcpState* st) { return reinterpret_cast<IcpDev*>(st + 1); }
 
-// Tail shared by the reductions: last CTA sums the partials in CTA order and (optionally) solves.
+// update = -(JtJ)^-1 Jtr; delta <- exp(update) * delta  (== exp(log(exp(update) exp(estimate))), Solver.cpp:110-111).
+// Executed by ONE FULL WARP (converged): lanes 0..5 each own a row of [JtJ | -Jtr] and run Gauss-Jordan
+// with the diagonal pivot (JtJ is SPD when the scene constrains all six degrees of freedom; otherwise the
+// result is not finite and the iteration stops); lanes 0..15 then own one element of the 4x4 product.
+__device__ __noinline__ void solveAndUpdateWarp(const float* sys, IcpState* st, IcpDev* dev, Counters* ctr, bool fixedPolicy) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    if (fixedPolicy ? !(sys[28] >= 6.0f) : (sys[27] == 0.0f)) {                 // CameraTracking.cpp:55-58
+        if (lane == 0) ctr->icpConverged = 1;
+        return;
+    }
+    double row[7];
+    const int r = lane < 6 ? lane : 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const int i = r < c ? r : c, j = r < c ? c : r;                         // upper-triangle index of (r, c)
+        row[c] = (double)sys[i * 6 - (i * (i - 1)) / 2 + (j - i)];              // selfadjointView, Solver.cpp:92
+    }
+    row[6] = -(double)sys[21 + r];                                             // update = -(JTJinv * JTr), :110
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double pr[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) pr[c] = __shfl_sync(full, row[c], k);
+        const double inv = 1.0 / pr[k];
+        if (lane != k) {
+            const double f = row[k] * inv;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) row[c] -= f * pr[c];
+        }
+    }
+    double x = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) if (r == c) x = row[6] / row[c];
+    const bool okLane = lane >= 6 || isfinite(x);
+    if (!__all_sync(full, okLane)) {
+        if (lane == 0) ctr->icpConverged = 1;
+        return;
+    }
+    double tw[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) tw[c] = __shfl_sync(full, x, c);
+    double A, B, C;
+    soTerms(tw + 3, A, B, C);                                                  // every lane, same values
+    const int i = (lane >> 2) & 3, j = lane & 3;
+    const double uij = se3ExpElement(tw, A, B, C, i, j);                        // lane l < 16 holds U[l]
+    double pij = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double uik = __shfl_sync(full, uij, i * 4 + k);
+        pij += uik * dev->D[k * 4 + j];
+    }
+    __syncwarp();                                                               // all reads of D before any write
+    if (lane < 16) { dev->D[lane] = pij; st->delta[lane] = (float)pij; }
+    if (lane == 0) st->iterations += 1;
+}
+
+// Tail shared by the reductions: the last CTA to arrive sums the per-CTA partials and (optionally) solves.
+// Each partial row is 32 floats = 8 x 16 bytes; thread t reads 16-byte column group (t & 7) of rows
+// (t >> 3), (t >> 3) + R, ... (R = blockDim/8; <= 3 independent loads for 148 CTAs x 512 threads), sums
+// them in fp64, and 32 threads add the R row-group sums in order.  Fixed order => deterministic.
 __device__ void reduceTail(const View& v, IcpState* st, float* partials, float tot, vh_icp_system* out, bool solve,
                            bool fixedPolicy) {
     __shared__ bool isLast;
     __shared__ float sSys[32];
-    __shared__ double sPart[8][32];
+    __shared__ double sRows[64][33];
     if (threadIdx.x < 32) partials[(size_t)blockIdx.x * 32 + threadIdx.x] = threadIdx.x < 29 ? tot : 0.f;
     __threadfence();
     __syncthreads();
@@ -204,55 +258,76 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
     __syncthreads();
     if (!isLast) return;
     __threadfence();
-    // All warps of the last CTA sum the per-CTA partials: warp g takes CTAs g, g+nw, ... (fixed order, fp64),
-    // lane = column; then the nw group sums are added in group order.  Deterministic for a given grid, and
-    // the loads of a thread are independent, so the L2 latency is paid a few times instead of gridDim times.
     {
-        const unsigned col = threadIdx.x & 31, grp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        double s = 0;
-        if (col < 29) {
-#pragma unroll 8
-            for (unsigned b = grp; b < gridDim.x; b += nw) s += (double)__ldcg(partials + (size_t)b * 32 + col);
+        const unsigned c4 = threadIdx.x & 7, r0 = threadIdx.x >> 3, R = blockDim.x >> 3;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll 4
+        for (unsigned b = r0; b < gridDim.x; b += R) {
+            const float4 p = __ldcg(reinterpret_cast<const float4*>(partials + (size_t)b * 32) + c4);
+            a0 += (double)p.x; a1 += (double)p.y; a2 += (double)p.z; a3 += (double)p.w;
         }
-        sPart[grp][col] = s;
+        sRows[r0][c4 * 4 + 0] = a0; sRows[r0][c4 * 4 + 1] = a1; sRows[r0][c4 * 4 + 2] = a2; sRows[r0][c4 * 4 + 3] = a3;
     }
     __syncthreads();
     if (threadIdx.x < 32) {
+        const unsigned R = blockDim.x >> 3;
         double t = 0;
-        for (unsigned g = 0; g < (blockDim.x >> 5); ++g) t += sPart[g][threadIdx.x];
-        sSys[threadIdx.x] = (float)t;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        st->system[threadIdx.x] = sSys[threadIdx.x];
-        if (out) reinterpret_cast<float*>(out)[threadIdx.x] = sSys[threadIdx.x];
-    }
-    if (threadIdx.x == 0) {
-        v.ctr->icpTicket = 0;
-        if (solve) solveAndUpdate(sSys, st, devOf(st), v.ctr, fixedPolicy);
+        for (unsigned g = 0; g < R; ++g) t += sRows[g][threadIdx.x];
+        const float f = (float)t;
+        sSys[threadIdx.x] = f;
+        st->system[threadIdx.x] = f;
+        if (out) reinterpret_cast<float*>(out)[threadIdx.x] = f;
+        if (threadIdx.x == 0) v.ctr->icpTicket = 0;
+        __syncwarp();
+        if (solve) solveAndUpdateWarp(sSys, st, devOf(st), v.ctr, fixedPolicy);
     }
 }
 
 template <class P>
-__global__ void __launch_bounds__(256) k_icp_iter(View v, IcpState* st, float* partials, const float4* __restrict__ in,
-                                                  const float4* __restrict__ inN, const float4* __restrict__ tg,
-                                                  const float4* __restrict__ tgN, int row0, int row1, vh_icp_system* out,
-                                                  int solve, int first) {
+__global__ void __launch_bounds__(kIcpThreads, 1) k_icp_iter(View v, IcpState* st, float* partials, const float4* __restrict__ in,
+                                                             const float4* __restrict__ inN, const float4* __restrict__ tg,
+                                                             const float4* __restrict__ tgN, int row0, int row1,
+                                                             vh_icp_system* out, int solve, int first) {
     __shared__ float sDelta[16];
-    __shared__ float sm[8][32];
-    if (!first && v.ctr->icpConverged) return;                 // uniform: the flag only changes in a tail
-    if (threadIdx.x < 16) sDelta[threadIdx.x] = st->delta[threadIdx.x];
+    __shared__ float sm[kIcpThreads / 32][32];
+    // both loads issue together; the flag only changes in a tail, so the early exit is uniform over the grid
+    const int conv = first ? 0 : v.ctr->icpConverged;
+    float dl = 0.f;
+    if (threadIdx.x < 16) dl = st->delta[threadIdx.x];
+    if (conv) return;
+    if (threadIdx.x < 16) sDelta[threadIdx.x] = dl;
     __syncthreads();
     float acc[29];
 #pragma unroll
     for (int k = 0; k < 29; ++k) acc[k] = 0.f;
     const int begin = row0 * v.W, end = row1 * v.W;
-    for (int i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
-        Corr c = associate<P>(v, sDelta, in, inN, tg, tgN, i);
-        if (!c.ok) continue;
-        const float3 a = P::fixed ? c.p : c.q;                 // ref Solver.cu:26 uses the TARGET point (Q23)
-        float J[6] = {c.n.x, c.n.y, c.n.z, a.y * c.n.z - a.z * c.n.y, a.z * c.n.x - a.x * c.n.z, a.x * c.n.y - a.y * c.n.x};
-        accumulate(acc, J, c.d);
+    const int T = gridDim.x * blockDim.x;
+    const bool haveM = P::fixed && inN != nullptr && v.icpNormalThres > -1.0f;
+    for (int i0 = begin + blockIdx.x * blockDim.x + threadIdx.x; i0 < end; i0 += 4 * T) {
+        Cand c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                       // 4 independent source loads in flight
+            const int idx = i0 + j * T;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < end) s = __ldg(in + idx);
+            c[j] = project<P>(v, sDelta, s);
+        }
+        float4 q[4], n[4], m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                       // then up to 12 independent gathers
+            q[j] = n[j] = m[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c[j].tidx >= 0) {
+                q[j] = __ldg(tg + c[j].tidx);
+                n[j] = __ldg(tgN + c[j].tidx);
+                if (haveM) m[j] = __ldg(inN + i0 + j * T);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (c[j].tidx < 0) continue;
+            Corr r = accept<P>(v, sDelta, c[j], q[j], n[j], m[j], haveM);
+            if (r.ok) accumulateCorr<P>(acc, r);
+        }
     }
     float tot = blockReduce29(acc, sm);
     if (first && threadIdx.x == 0 && blockIdx.x == 0) v.ctr->icpConverged = 0;
@@ -356,12 +431,13 @@ __global__ void __launch_bounds__(128) k_linear_system_300(int n, const float4* 
 }
 
 __global__ void k_icp_solve(View v, IcpState* st, const vh_icp_system* sys, int fixedPolicy) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ float s[32];
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     if (v.ctr->icpConverged) return;
-    float s[32];
-    for (int i = 0; i < 32; ++i) s[i] = reinterpret_cast<const float*>(sys)[i];
-    for (int i = 0; i < 32; ++i) st->system[i] = s[i];
-    solveAndUpdate(s, st, devOf(st), v.ctr, fixedPolicy != 0);
+    s[threadIdx.x] = reinterpret_cast<const float*>(sys)[threadIdx.x];
+    st->system[threadIdx.x] = s[threadIdx.x];
+    __syncwarp();
+    solveAndUpdateWarp(s, st, devOf(st), v.ctr, fixedPolicy != 0);
 }
 
 struct Twist6 { float t[6]; };
@@ -391,9 +467,9 @@ __global__ void k_icp_twist(IcpState* st) {                    // Solver::estima
     for (int i = 0; i < 6; ++i) st->twist[i] = (float)tw[i];
 }
 
-static int icpGrid(const vh_context* c, int pixels) {
-    int g = (pixels + 255) / 256;
-    int cap = c->numSMs * 2;
+static int icpGrid(const vh_context* c, int pixels, int threads, int perSM) {
+    int g = (pixels + threads - 1) / threads;
+    int cap = c->numSMs * perSM;
     if (cap > kIcpMaxBlocks) cap = kIcpMaxBlocks;
     if (g > cap) g = cap;
     return g < 1 ? 1 : g;
@@ -406,11 +482,11 @@ cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, 
 
 cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                int row0, int row1, vh_icp_system* d_out, bool solve, bool first, cudaStream_t s) {
-    int g = icpGrid(c, (row1 - row0) * c->v.W);
+    int g = icpGrid(c, ((row1 - row0) * c->v.W + 3) / 4, kIcpThreads, 1);     // one CTA per SM, 4 pixels per thread per trip
     if (c->cfg.policy == VH_POLICY_FIXED)
-        k_icp_iter<Fixed><<<g, 256, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first);
+        k_icp_iter<Fixed><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first);
     else
-        k_icp_iter<RefExact><<<g, 256, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first);
+        k_icp_iter<RefExact><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first);
     return cudaGetLastError();
 }
 
@@ -443,20 +519,20 @@ cudaError_t launch_find_corr(vh_context* c, const float4* in, const float4* inN,
     for (int i = 0; i < 16; ++i) d.m[i] = delta16_host[i];
     cudaError_t e = cudaMemsetAsync(d_err, 0, sizeof(float), s);     // ref :193
     if (e != cudaSuccess) return e;
-    int g = icpGrid(c, c->v.W * c->v.H);
+    int g = icpGrid(c, c->v.W * c->v.H, 256, 4);
     if (c->cfg.policy == VH_POLICY_FIXED) k_find_corr<Fixed><<<g, 256, 0, s>>>(c->v, d, in, inN, tg, tgN, corr, corrN, res, d_err);
     else k_find_corr<RefExact><<<g, 256, 0, s>>>(c->v, d, in, inN, tg, tgN, corr, corrN, res, d_err);
     return cudaGetLastError();
 }
 
 cudaError_t launch_jacobians(vh_context* c, const float4* corr, const float4* corrN, float* J, cudaStream_t s) {
-    k_jacobians<<<icpGrid(c, c->v.W * c->v.H), 256, 0, s>>>(c->v, corr, corrN, J);
+    k_jacobians<<<icpGrid(c, c->v.W * c->v.H, 256, 4), 256, 0, s>>>(c->v, corr, corrN, J);
     return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_corr(vh_context* c, const float4* corr, const float4* corrN, const float* res, vh_icp_system* d_out,
                                cudaStream_t s) {
-    k_reduce_corr<<<icpGrid(c, c->v.W * c->v.H), 256, 0, s>>>(c->v, c->icp, c->icpPartials, corr, corrN, res, d_out);
+    k_reduce_corr<<<icpGrid(c, c->v.W * c->v.H, 256, 2), 256, 0, s>>>(c->v, c->icp, c->icpPartials, corr, corrN, res, d_out);
     return cudaGetLastError();
 }
 
