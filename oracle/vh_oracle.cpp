@@ -703,9 +703,10 @@ inline Corr associate(const vo_config& c, const float* input, const float* input
     V4 p = mul4(delta, V4{s[0], s[1], s[2], 1.0f});
     if (!(p.z > 0.0f)) return r;
     const float fx = c.K[0], fy = c.K[4], cx = c.K[2], cy = c.K[5];
-    float u = (fx * p.x + cx * p.z) / p.z, v = (fy * p.y + cy * p.z) / p.z;
-    if (!(u >= -0.5f && u < (float)W - 0.5f && v >= -0.5f && v < (float)H - 0.5f)) return r;
-    int ix = std::min((int)(u + 0.5f), W - 1), iy = std::min((int)(v + 0.5f), H - 1);
+    float iz = 1.0f / p.z;
+    float u = fmaf(p.x * iz, fx, cx), v = fmaf(p.y * iz, fy, cy);
+    int ix = f2i_rn(u), iy = f2i_rn(v);                                         // nearest pixel, ties to even (as integrate)
+    if ((unsigned)ix >= (unsigned)W || (unsigned)iy >= (unsigned)H) return r;
     const float* q = target + (size_t)(iy * W + ix) * 4;
     const float* n = targetNormals + (size_t)(iy * W + ix) * 4;
     if (!(q[2] > 0.0f)) return r;

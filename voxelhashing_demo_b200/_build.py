@@ -32,7 +32,7 @@ NVCC_FLAGS = [
     "-ccbin", HOSTCXX,
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default",
     "-I", str(ROOT / "include"), "-I", str(CSRC),
-]
+] + os.environ.get("VH_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DVH_ICP_TRACE for tools/icp_trace.py
 
 
 def _sources() -> list[Path]:

@@ -23,6 +23,20 @@ namespace vh {
 
 constexpr int kIcpThreads = 512;
 
+#ifdef VH_ICP_TRACE
+__device__ unsigned long long g_icpTrace[1024 * 8];
+__device__ __forceinline__ void trace(int slot) {
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_icpTrace[blockIdx.x * 8 + slot] = t;
+    }
+}
+#define VH_TRACE(slot) trace(slot)
+#else
+#define VH_TRACE(slot)
+#endif
+
 struct Cand { float3 p; int tidx; };             // transformed source point and target pixel (-1: none)
 struct Corr { bool ok; float3 q, n, p; float d; float qw, nw; };
 
@@ -45,9 +59,10 @@ __device__ __forceinline__ Cand project(const View& v, const float* __restrict__
     if (!(s.z > 0.0f)) return c;
     float4 p = mul4(delta, s.x, s.y, s.z, 1.0f);
     if (!(p.z > 0.0f)) return c;
-    float u = (v.fx * p.x + v.cx * p.z) / p.z, w = (v.fy * p.y + v.cy * p.z) / p.z;
-    if (!(u >= -0.5f && u < (float)v.W - 0.5f && w >= -0.5f && w < (float)v.H - 0.5f)) return c;
-    int ix = min((int)(u + 0.5f), v.W - 1), iy = min((int)(w + 0.5f), v.H - 1);
+    const float rz = __frcp_rn(p.z);                                            // == 1.0f / p.z, correctly rounded
+    const float u = fmaf(p.x * rz, v.fx, v.cx), w = fmaf(p.y * rz, v.fy, v.cy);
+    const int ix = __float2int_rn(u), iy = __float2int_rn(w);                  // nearest pixel, ties to even (as integrate)
+    if ((unsigned)ix >= (unsigned)v.W || (unsigned)iy >= (unsigned)v.H) return c;
     c.p = make_float3(p.x, p.y, p.z);
     c.tidx = iy * v.W + ix;
     return c;
@@ -118,13 +133,26 @@ __device__ __forceinline__ void accumulateCorr(float* acc, const Corr& c) {
 }
 
 // CTA reduction of 29 sums; result valid in warp 0 lane k (k < 29) as the return value.
+// Warp stage: transpose-reduce.  A shuffle tree per value costs 29 x 5 = 145 SHFL per warp and the SHFL
+// pipe (one warp-instruction per cycle per SM) was the bottleneck of the block reduce (r1b trace: 1.5 us).
+// Here lane pairs exchange the HALF of the values they do not keep: 16 + 8 + 4 + 2 + 1 = 31 SHFL, after
+// which lane L holds the warp total of value L.
 __device__ __forceinline__ float blockReduce29(float* acc, float (*sm)[32]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float t[32];
 #pragma unroll
-    for (int k = 0; k < 29; ++k) {
-        float s = warpSum(acc[k]);
-        if (lane == 0) sm[warp][k] = s;
+    for (int k = 0; k < 32; ++k) t[k] = k < 29 ? acc[k] : 0.f;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const bool upper = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < step; ++i) {
+            const float send = upper ? t[i] : t[i + step];
+            const float keep = upper ? t[i + step] : t[i];
+            t[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
     }
+    sm[warp][lane] = t[0];
     __syncthreads();
     float tot = 0.f;
     if (warp == 0 && lane < 29) {
@@ -186,37 +214,48 @@ struct IcpDev {               // device-resident solver state (Solver::estimate 
 __device__ __forceinline__ IcpDev* devOf(IcpState* st) { return reinterpret_cast<IcpDev*>(st + 1); }
 
 // update = -(JtJ)^-1 Jtr; delta <- exp(update) * delta  (== exp(log(exp(update) exp(estimate))), Solver.cpp:110-111).
-// Executed by ONE FULL WARP (converged): lanes 0..5 each own a row of [JtJ | -Jtr] and run Gauss-Jordan
-// with the diagonal pivot (JtJ is SPD when the scene constrains all six degrees of freedom; otherwise the
-// result is not finite and the iteration stops); lanes 0..15 then own one element of the 4x4 product.
+// Executed by ONE FULL WARP (converged).  r1b trace: the fp64 form of this step cost 3.4 us of a 13.6 us
+// iteration (software fp64 division / sincos on one dependent chain), so:
+//   * lanes 0..5 each own a row of [JtJ | -Jtr] and run Gauss-Jordan with the diagonal pivot in fp32 (JtJ is
+//     SPD when the scene constrains all six degrees of freedom; otherwise the result is not finite and the
+//     iteration stops).  Gauss-Newton is self-correcting: an fp32 error in one update is removed by the next;
+//   * lanes 0..15 own one element of exp(update) (fp32, series below 0.05 rad) and of the 4x4 product, which
+//     is accumulated in fp64 into the fp64 state D;
+//   * one Newton-Schulz step R <- 1.5 R - 0.5 R R^T R (fp64) re-orthonormalises the rotation, so the fp32
+//     rounding of exp(update) cannot accumulate over the thousands of updates of a long sequence.
 __device__ __noinline__ void solveAndUpdateWarp(const float* sys, IcpState* st, IcpDev* dev, Counters* ctr, bool fixedPolicy) {
+    __shared__ double sP[16];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     if (fixedPolicy ? !(sys[28] >= 6.0f) : (sys[27] == 0.0f)) {                 // CameraTracking.cpp:55-58
         if (lane == 0) ctr->icpConverged = 1;
         return;
     }
-    double row[7];
+    // the fp64 state is only needed at the very end: put its loads in flight before the elimination
+    double dcol[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dcol[k] = __ldcg(dev->D + k * 4 + (lane & 3));
+    float row[7];
     const int r = lane < 6 ? lane : 0;
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
         const int i = r < c ? r : c, j = r < c ? c : r;                         // upper-triangle index of (r, c)
-        row[c] = (double)sys[i * 6 - (i * (i - 1)) / 2 + (j - i)];              // selfadjointView, Solver.cpp:92
+        row[c] = sys[i * 6 - (i * (i - 1)) / 2 + (j - i)];                      // selfadjointView, Solver.cpp:92
     }
-    row[6] = -(double)sys[21 + r];                                             // update = -(JTJinv * JTr), :110
+    row[6] = -sys[21 + r];                                                     // update = -(JTJinv * JTr), :110
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        double pr[7];
+        float pr[7];
 #pragma unroll
         for (int c = 0; c < 7; ++c) pr[c] = __shfl_sync(full, row[c], k);
-        const double inv = 1.0 / pr[k];
+        const float inv = 1.0f / pr[k];
         if (lane != k) {
-            const double f = row[k] * inv;
+            const float f = row[k] * inv;
 #pragma unroll
             for (int c = 0; c < 7; ++c) row[c] -= f * pr[c];
         }
     }
-    double x = 0.0;
+    float x = 0.0f;
 #pragma unroll
     for (int c = 0; c < 6; ++c) if (r == c) x = row[6] / row[c];
     const bool okLane = lane >= 6 || isfinite(x);
@@ -224,22 +263,58 @@ __device__ __noinline__ void solveAndUpdateWarp(const float* sys, IcpState* st, 
         if (lane == 0) ctr->icpConverged = 1;
         return;
     }
-    double tw[6];
+    float tw[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) tw[c] = __shfl_sync(full, x, c);
-    double A, B, C;
-    soTerms(tw + 3, A, B, C);                                                  // every lane, same values
+    // exp([[w]x v; 0 0]) element (i, j), fp32 (ref SE3Exp, twist = (v, omega)); every lane, same A, B, C
+    const float t2 = tw[3] * tw[3] + tw[4] * tw[4] + tw[5] * tw[5];
+    float A, B, C;
+    if (t2 < 2.5e-3f) {
+        A = 1.0f - t2 * (1.0f / 6.0f) + t2 * t2 * (1.0f / 120.0f);
+        B = 0.5f - t2 * (1.0f / 24.0f) + t2 * t2 * (1.0f / 720.0f);
+        C = (1.0f / 6.0f) - t2 * (1.0f / 120.0f) + t2 * t2 * (1.0f / 5040.0f);
+    } else {
+        const float th = sqrtf(t2);
+        float sn, cs;
+        sincosf(th, &sn, &cs);
+        A = sn / th; B = (1.0f - cs) / t2; C = (th - sn) / (t2 * th);
+    }
     const int i = (lane >> 2) & 3, j = lane & 3;
-    const double uij = se3ExpElement(tw, A, B, C, i, j);                        // lane l < 16 holds U[l]
+    float uij;
+    {
+        const float K[9] = {0.f, -tw[5], tw[4], tw[5], 0.f, -tw[3], -tw[4], tw[3], 0.f};
+        const int ii = i < 3 ? i : 0;
+        float K2row[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) K2row[c] = K[ii * 3] * K[c] + K[ii * 3 + 1] * K[3 + c] + K[ii * 3 + 2] * K[6 + c];
+        float rot = 0.f, tr = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float I = ii == c ? 1.0f : 0.0f;
+            if (c == j) rot = I + A * K[ii * 3 + c] + B * K2row[c];
+            tr += (I + B * K[ii * 3 + c] + C * K2row[c]) * tw[c];
+        }
+        uij = i == 3 ? (j == 3 ? 1.0f : 0.0f) : (j < 3 ? rot : tr);
+    }
     double pij = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const double uik = __shfl_sync(full, uij, i * 4 + k);
-        pij += uik * dev->D[k * 4 + j];
+        const float uik = __shfl_sync(full, uij, i * 4 + k);
+        pij += (double)uik * dcol[k];
     }
-    __syncwarp();                                                               // all reads of D before any write
+    if (lane < 16) sP[lane] = pij;
+    __syncwarp();
+    if (lane < 16 && i < 3 && j < 3) {                                          // Newton-Schulz on the rotation block
+        double rm = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double mkj = sP[0 * 4 + k] * sP[0 * 4 + j] + sP[1 * 4 + k] * sP[1 * 4 + j] + sP[2 * 4 + k] * sP[2 * 4 + j];
+            rm += sP[i * 4 + k] * mkj;
+        }
+        pij = 1.5 * pij - 0.5 * rm;
+    }
     if (lane < 16) { dev->D[lane] = pij; st->delta[lane] = (float)pij; }
-    if (lane == 0) st->iterations += 1;
+    if (lane == 0) atomicAdd(&st->iterations, 1);            // RED: nothing waits for it
 }
 
 // Tail shared by the reductions: the last CTA to arrive sums the per-CTA partials and (optionally) solves.
@@ -256,6 +331,7 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
     __syncthreads();
     if (threadIdx.x == 0) isLast = atomicAdd(&v.ctr->icpTicket, 1u) == gridDim.x - 1;
     __syncthreads();
+    VH_TRACE(4);
     if (!isLast) return;
     __threadfence();
     {
@@ -269,6 +345,7 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
         sRows[r0][c4 * 4 + 0] = a0; sRows[r0][c4 * 4 + 1] = a1; sRows[r0][c4 * 4 + 2] = a2; sRows[r0][c4 * 4 + 3] = a3;
     }
     __syncthreads();
+    VH_TRACE(5);
     if (threadIdx.x < 32) {
         const unsigned R = blockDim.x >> 3;
         double t = 0;
@@ -279,7 +356,9 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
         if (out) reinterpret_cast<float*>(out)[threadIdx.x] = f;
         if (threadIdx.x == 0) v.ctr->icpTicket = 0;
         __syncwarp();
+        VH_TRACE(6);
         if (solve) solveAndUpdateWarp(sSys, st, devOf(st), v.ctr, fixedPolicy);
+        VH_TRACE(7);
     }
 }
 
@@ -291,30 +370,37 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_iter(View v, IcpState* s
     __shared__ float sDelta[16];
     __shared__ float sm[kIcpThreads / 32][32];
     // both loads issue together; the flag only changes in a tail, so the early exit is uniform over the grid
+    VH_TRACE(0);
+    constexpr int B = 5;                                    // pixels in flight per thread: 148 x 512 x 5 >= 640 x 480 in ONE trip
+    const int begin = row0 * v.W, end = row1 * v.W;
+    const int T = gridDim.x * blockDim.x;
+    int i0 = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    // the flag, delta and the first batch of source vertices are independent loads: issue them together
     const int conv = first ? 0 : v.ctr->icpConverged;
     float dl = 0.f;
     if (threadIdx.x < 16) dl = st->delta[threadIdx.x];
-    if (conv) return;
+    float4 s[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        const int idx = i0 + j * T;
+        s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < end) s[j] = __ldg(in + idx);
+    }
+    if (conv) return;                                       // uniform over the grid: the flag only changes in a tail
     if (threadIdx.x < 16) sDelta[threadIdx.x] = dl;
     __syncthreads();
+    VH_TRACE(1);
     float acc[29];
 #pragma unroll
     for (int k = 0; k < 29; ++k) acc[k] = 0.f;
-    const int begin = row0 * v.W, end = row1 * v.W;
-    const int T = gridDim.x * blockDim.x;
     const bool haveM = P::fixed && inN != nullptr && v.icpNormalThres > -1.0f;
-    for (int i0 = begin + blockIdx.x * blockDim.x + threadIdx.x; i0 < end; i0 += 4 * T) {
-        Cand c[4];
+    while (true) {
+        Cand c[B];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                       // 4 independent source loads in flight
-            const int idx = i0 + j * T;
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < end) s = __ldg(in + idx);
-            c[j] = project<P>(v, sDelta, s);
-        }
-        float4 q[4], n[4], m[4];
+        for (int j = 0; j < B; ++j) c[j] = project<P>(v, sDelta, s[j]);
+        float4 q[B], n[B], m[B];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                       // then up to 12 independent gathers
+        for (int j = 0; j < B; ++j) {                       // up to 3 B independent gathers
             q[j] = n[j] = m[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c[j].tidx >= 0) {
                 q[j] = __ldg(tg + c[j].tidx);
@@ -322,17 +408,36 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_iter(View v, IcpState* s
                 if (haveM) m[j] = __ldg(inN + i0 + j * T);
             }
         }
+        i0 += B * T;
+        const bool more = i0 < end;                          // larger images: next batch of sources goes in flight now
+        if (more) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < B; ++j) {
+                const int idx = i0 + j * T;
+                s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < end) s[j] = __ldg(in + idx);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
             if (c[j].tidx < 0) continue;
             Corr r = accept<P>(v, sDelta, c[j], q[j], n[j], m[j], haveM);
             if (r.ok) accumulateCorr<P>(acc, r);
         }
+        if (!more) break;
     }
+    VH_TRACE(2);
     float tot = blockReduce29(acc, sm);
+    VH_TRACE(3);
     if (first && threadIdx.x == 0 && blockIdx.x == 0) v.ctr->icpConverged = 0;
     reduceTail(v, st, partials, tot, out, solve != 0, P::fixed);
 }
+
+#ifdef VH_ICP_TRACE
+extern "C" int vh_icp_trace_read(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_icpTrace, sizeof(unsigned long long) * n);
+}
+#endif
 
 // Normal equations from stored correspondences (the arrays computeCorrespondences leaves behind):
 // what Solver::BuildLinearSystem computes with Sgemv/Ssyrk (ref Solver.cpp:80-94).
@@ -482,7 +587,7 @@ cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, 
 
 cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                int row0, int row1, vh_icp_system* d_out, bool solve, bool first, cudaStream_t s) {
-    int g = icpGrid(c, ((row1 - row0) * c->v.W + 3) / 4, kIcpThreads, 1);     // one CTA per SM, 4 pixels per thread per trip
+    int g = icpGrid(c, (row1 - row0) * c->v.W, kIcpThreads, 1);               // one CTA per SM; VGA = 4.05 pixels per thread, one trip of <= 5
     if (c->cfg.policy == VH_POLICY_FIXED)
         k_icp_iter<Fixed><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first);
     else
