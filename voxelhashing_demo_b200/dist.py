@@ -66,7 +66,7 @@ class PartitionedTracker:
         if self.rank == 0:
             self.depth.copy_(d_depth.view(self.depth.dtype))
         if self.world > 1:
-            dist.broadcast(self.depth.view(self.torch.int16), src=0, group=self.group)   # NVLink / NVSwitch
+            dist.broadcast(self.depth.view(self.torch.uint8), src=0, group=self.group)   # raw bytes over NVLink / NVSwitch
         par = self.frame & 1
         v, n, df = self.maps[par]
         pv, pn, _ = self.maps[1 - par]
