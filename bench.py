@@ -364,6 +364,7 @@ def run_multi(args, rank, world, local):
     from voxelhashing_demo_b200 import Context
     from voxelhashing_demo_b200.dist import PartitionedTracker
 
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name = args.workload or "C4"
     cfg, scene, traj, seq_len = workload_config(name, world, rank)
@@ -411,7 +412,8 @@ def run_multi(args, rank, world, local):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{name}: large-volume {cfg.width}x{cfg.height} sequence (scene S3), voxel {cfg.voxelSize} m, hash space "
-                                   f"partitioned over {world} GPUs (owner = mix(block) mod {world}), NCCL frame broadcast + 32-float ICP all-reduce",
+                                   f"partitioned over {world} GPUs (owner = mix(block) mod {world}), NCCL frame broadcast, 32-float ICP all-reduce "
+                                   + ("FUSED into the ICP kernel epilogue over NVLink peer memory" if tracker.fused else "through NCCL"),
                        "l2": "per-frame voxel working set exceeds L2 on every rank",
                        "final_pose_translation_error_m": float(np.max(np.abs(pose[:3, 3] - truth[:3, 3]))),
                        "visible_blocks_all_ranks": int(counts[1].item()), "allocated_blocks_all_ranks": int(counts[2].item())},

@@ -200,6 +200,16 @@ int vh_icp_align(vh_context* ctx, const float4* d_input, const float4* d_inputNo
 int vh_icp_reduce(vh_context* ctx, const float4* d_input, const float4* d_inputNormals,
                   const float4* d_target, const float4* d_targetNormals,
                   int row0, int row1, vh_icp_system* d_system, vh_stream s);
+/* Multi-GPU, fused form: register the peer-mapped exchange regions (one per rank, vh_peer_bytes() each,
+ * zero-initialised; bufs[p] = rank p's region as mapped into this process, world <= 8), then
+ * vh_icp_align_rows runs `iterations` Gauss-Newton iterations over this rank's rows with the all-reduce of
+ * the 32-float system fused into each kernel's epilogue (P2P stores + sequence-numbered flags over NVLink);
+ * every rank ends with the bit-identical delta. */
+int vh_set_peers(vh_context* ctx, int rank, int world, void* const* bufs);
+unsigned long long vh_peer_bytes(void);
+int vh_icp_align_rows(vh_context* ctx, const float4* d_input, const float4* d_inputNormals,
+                      const float4* d_target, const float4* d_targetNormals, int row0, int row1,
+                      int iterations, vh_stream s);
 /* Solve + SE(3) update from an (all-reduced) system in device memory. */
 int vh_icp_solve(vh_context* ctx, const vh_icp_system* d_system, vh_stream s);
 /* Synchronises; delta: 16 floats row-major (input frame -> target frame), twist: 6 floats (v, omega). */

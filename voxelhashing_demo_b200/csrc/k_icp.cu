@@ -321,8 +321,48 @@ __device__ __noinline__ void solveAndUpdateWarp(const float* sys, IcpState* st, 
 // Each partial row is 32 floats = 8 x 16 bytes; thread t reads 16-byte column group (t & 7) of rows
 // (t >> 3), (t >> 3) + R, ... (R = blockDim/8; <= 3 independent loads for 148 CTAs x 512 threads), sums
 // them in fp64, and 32 threads add the R row-group sums in order.  Fixed order => deterministic.
+// ---- fused cross-GPU all-reduce (one process per GPU, peer memory over NVLink / NVSwitch) --------------
+__device__ __forceinline__ void stReleaseSys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ldAcquireSys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ldRelaxedSys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+// Warp 0 of the last CTA: scatter this rank's 32 partial sums into every rank's exchange region (P2P
+// stores), publish a sequence-numbered flag, wait for all ranks' flags, add the contributions in RANK
+// ORDER (so every rank holds the bit-identical system and solves the identical pose: no second broadcast).
+// Regions are double-buffered on the sequence parity: a rank can run at most one exchange ahead of the
+// slowest rank, because it cannot finish exchange k+1 without that rank's contribution to k+1.
+__device__ void peerAllReduce(const PeerView& pv, Counters* ctr, float* sSys) {
+    const int lane = threadIdx.x & 31;
+    unsigned seq = 0;
+    if (lane == 0) seq = ctr->icpSeq + 1;
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    const unsigned slot = seq & 1u;
+    const float mine = sSys[lane];
+    for (int p = 0; p < pv.world; ++p) pv.buf[p][(slot * kMaxPeers + pv.rank) * 32 + lane] = mine;
+    __threadfence_system();
+    __syncwarp();
+    if (lane < pv.world) stReleaseSys(reinterpret_cast<unsigned*>(pv.buf[lane] + kPeerDataFloats) + slot * kMaxPeers + pv.rank, seq);
+    if (lane < pv.world) {
+        const unsigned* f = reinterpret_cast<const unsigned*>(pv.buf[pv.rank] + kPeerDataFloats) + slot * kMaxPeers + lane;
+        while (ldAcquireSys(f) != seq) { }
+    }
+    __syncwarp();
+    float t = 0.f;
+    for (int r = 0; r < pv.world; ++r) t += ldRelaxedSys(pv.buf[pv.rank] + (slot * kMaxPeers + r) * 32 + lane);
+    sSys[lane] = t;
+    if (lane == 0) ctr->icpSeq = seq;
+    __syncwarp();
+}
+
 __device__ void reduceTail(const View& v, IcpState* st, float* partials, float tot, vh_icp_system* out, bool solve,
-                           bool fixedPolicy) {
+                           bool fixedPolicy, const PeerView* pv = nullptr) {
     __shared__ bool isLast;
     __shared__ float sSys[32];
     __shared__ double sRows[64][33];
@@ -350,11 +390,16 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
         const unsigned R = blockDim.x >> 3;
         double t = 0;
         for (unsigned g = 0; g < R; ++g) t += sRows[g][threadIdx.x];
-        const float f = (float)t;
+        float f = (float)t;
         sSys[threadIdx.x] = f;
+        if (threadIdx.x == 0) v.ctr->icpTicket = 0;
+        __syncwarp();
+        if (pv != nullptr && pv->world > 1) {                // the collective, fused into the epilogue
+            peerAllReduce(*pv, v.ctr, sSys);
+            f = sSys[threadIdx.x];
+        }
         st->system[threadIdx.x] = f;
         if (out) reinterpret_cast<float*>(out)[threadIdx.x] = f;
-        if (threadIdx.x == 0) v.ctr->icpTicket = 0;
         __syncwarp();
         VH_TRACE(6);
         if (solve) solveAndUpdateWarp(sSys, st, devOf(st), v.ctr, fixedPolicy);
@@ -366,7 +411,7 @@ template <class P>
 __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_iter(View v, IcpState* st, float* partials, const float4* __restrict__ in,
                                                              const float4* __restrict__ inN, const float4* __restrict__ tg,
                                                              const float4* __restrict__ tgN, int row0, int row1,
-                                                             vh_icp_system* out, int solve, int first) {
+                                                             vh_icp_system* out, int solve, int first, PeerView pv) {
     __shared__ float sDelta[16];
     __shared__ float sm[kIcpThreads / 32][32];
     // both loads issue together; the flag only changes in a tail, so the early exit is uniform over the grid
@@ -430,7 +475,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_iter(View v, IcpState* s
     float tot = blockReduce29(acc, sm);
     VH_TRACE(3);
     if (first && threadIdx.x == 0 && blockIdx.x == 0) v.ctr->icpConverged = 0;
-    reduceTail(v, st, partials, tot, out, solve != 0, P::fixed);
+    reduceTail(v, st, partials, tot, out, solve != 0, P::fixed, &pv);
 }
 
 #ifdef VH_ICP_TRACE
@@ -588,10 +633,23 @@ cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, 
 cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                int row0, int row1, vh_icp_system* d_out, bool solve, bool first, cudaStream_t s) {
     int g = icpGrid(c, (row1 - row0) * c->v.W, kIcpThreads, 1);               // one CTA per SM; VGA = 4.05 pixels per thread, one trip of <= 5
+    PeerView none{};
+    none.world = 1;
     if (c->cfg.policy == VH_POLICY_FIXED)
-        k_icp_iter<Fixed><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first);
+        k_icp_iter<Fixed><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first, none);
     else
-        k_icp_iter<RefExact><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first);
+        k_icp_iter<RefExact><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first, none);
+    return cudaGetLastError();
+}
+
+// One iteration over this rank's image rows with the all-reduce fused into the kernel's epilogue.
+cudaError_t launch_icp_iter_peer(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
+                                 int row0, int row1, bool first, cudaStream_t s) {
+    int g = icpGrid(c, (row1 - row0) * c->v.W, kIcpThreads, 1);
+    if (c->cfg.policy == VH_POLICY_FIXED)
+        k_icp_iter<Fixed><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, nullptr, 1, first, c->peers);
+    else
+        k_icp_iter<RefExact><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, nullptr, 1, first, c->peers);
     return cudaGetLastError();
 }
 

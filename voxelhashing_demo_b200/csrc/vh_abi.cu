@@ -127,6 +127,7 @@ int vh_create(const vh_config* cfg, vh_context** out) {
     vh_context* c = new vh_context();
     memset(static_cast<void*>(c), 0, sizeof(*c));
     c->cfg = *cfg;
+    c->peers.world = 1;
     if (c->cfg.policy == VH_POLICY_FIXED && c->cfg.overflowSlots == 0) c->cfg.overflowSlots = c->cfg.table.numBuckets;
     if (c->cfg.partCount < 1) c->cfg.partCount = 1;
     cudaGetDevice(&c->device);
@@ -298,6 +299,28 @@ int vh_icp_reduce(vh_context* c, const float4* in, const float4* inN, const floa
     VH_CUDA(launch_icp_iter_ex(c, in, inN, tg, tgN, row0, row1, d_system, false, true, S(s)));
     return VH_OK;
 }
+// Multi-GPU: peer-mapped exchange regions (one per rank, VH_PEER_BYTES each, zero-initialised), e.g. from
+// torch.distributed._symmetric_memory or cudaIpc.  bufs[p] = rank p's region as visible from THIS process.
+int vh_set_peers(vh_context* c, int rank, int world, void* const* bufs) {
+    if (!c || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || (world > 1 && !bufs))
+        return fail(VH_ERR_INVALID, "vh_set_peers: bad argument (world <= 8)");
+    c->peers.world = world;
+    c->peers.rank = rank;
+    for (int p = 0; p < kMaxPeers; ++p) c->peers.buf[p] = (p < world && bufs) ? static_cast<float*>(bufs[p]) : nullptr;
+    return VH_OK;
+}
+unsigned long long vh_peer_bytes(void) { return (unsigned long long)kPeerBytes; }
+
+// Align over this rank's rows [row0,row1) with the cross-GPU all-reduce fused into every iteration's kernel.
+int vh_icp_align_rows(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN, int row0, int row1,
+                      int iterations, vh_stream s) {
+    if (!c || !in || !tg || !tgN) return fail(VH_ERR_INVALID, "vh_icp_align_rows: null argument");
+    if (row0 < 0 || row1 > c->v.H || row0 > row1) return fail(VH_ERR_INVALID, "vh_icp_align_rows: bad row range");
+    if (iterations <= 0) iterations = c->cfg.icpIterations;
+    for (int it = 0; it < iterations; ++it) VH_CUDA(launch_icp_iter_peer(c, in, inN, tg, tgN, row0, row1, it == 0, S(s)));
+    return VH_OK;
+}
+
 int vh_icp_solve(vh_context* c, const vh_icp_system* d_system, vh_stream s) {
     if (!c || !d_system) return fail(VH_ERR_INVALID, "vh_icp_solve: null argument");
     VH_CUDA(launch_icp_solve(c, d_system, S(s)));

@@ -33,7 +33,7 @@ struct Counters {
     int lastInserted;
     int icpConverged;             // set when the residual sum is exactly 0 (CameraTracking.cpp:55)
     unsigned int icpTicket;       // last-CTA-done ticket of the ICP reduction
-    int pad0;
+    unsigned int icpSeq;          // sequence number of the fused cross-GPU exchange in the ICP tail
     unsigned long long numUpdated;
 };
 
@@ -76,6 +76,13 @@ struct View {
 
 constexpr int kIcpMaxBlocks = 1024;
 
+// Fused all-reduce of the ICP normal equations over NVLink peer memory.
+// buf[p] = rank p's exchange region mapped into this process: float data[2][8][32], then unsigned flag[2][8].
+constexpr int kMaxPeers = 8;
+constexpr int kPeerDataFloats = 2 * kMaxPeers * 32;
+constexpr size_t kPeerBytes = (kPeerDataFloats + 2 * kMaxPeers) * 4;
+struct PeerView { int world, rank; float* buf[kMaxPeers]; };
+
 struct Pose16f { float m[16]; };
 
 }  // namespace vh
@@ -91,6 +98,7 @@ struct vh_context {
     size_t bytesAllocated;
     // host-visible copy of the RefExact fusion-side projection flag etc.
     bool intrinsicsSet;
+    vh::PeerView peers;       // world <= 1: single GPU
 };
 
 namespace vh {
@@ -109,6 +117,8 @@ cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, 
 cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                int row0, int row1, vh_icp_system* d_out, bool solve, bool first, cudaStream_t s);
 cudaError_t launch_icp_solve(vh_context* c, const vh_icp_system* d_sys, cudaStream_t s);
+cudaError_t launch_icp_iter_peer(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
+                                 int row0, int row1, bool first, cudaStream_t s);
 cudaError_t launch_icp_reset(vh_context* c, bool resetDelta, cudaStream_t s);
 cudaError_t launch_icp_set_twist(vh_context* c, const float* twist6, cudaStream_t s);
 cudaError_t launch_icp_twist(vh_context* c, cudaStream_t s);

@@ -199,6 +199,18 @@ class Context:
     def icp_reduce(self, inp, inpN, tgt, tgtN, row0, row1, d_system, stream=None):
         L.check(self.lib.vh_icp_reduce(self._h, _ptr(inp), _ptr(inpN), _ptr(tgt), _ptr(tgtN), row0, row1, _ptr(d_system), _stream(stream)))
 
+    def set_peers(self, rank: int, world: int, peer_ptrs):
+        """Register the peer-mapped exchange regions for the fused cross-GPU all-reduce of the ICP tail."""
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        L.check(self.lib.vh_set_peers(self._h, rank, world, arr), "vh_set_peers")
+
+    def peer_bytes(self) -> int:
+        return int(self.lib.vh_peer_bytes())
+
+    def icp_align_rows(self, inp, inpN, tgt, tgtN, row0, row1, iterations=0, stream=None):
+        L.check(self.lib.vh_icp_align_rows(self._h, _ptr(inp), _ptr(inpN), _ptr(tgt), _ptr(tgtN), row0, row1, iterations,
+                                           _stream(stream)), "vh_icp_align_rows")
+
     def icp_solve(self, d_system, stream=None):
         L.check(self.lib.vh_icp_solve(self._h, _ptr(d_system), _stream(stream)))
 
