@@ -38,6 +38,15 @@ sys.path.insert(0, str(ROOT))
 METRIC = "VGA frames/s (alloc+integrate+ICP)"
 UNIT = "frames/s"
 
+# Libraries print to stdout behind our back (NCCL's version banner, the reference's std::cout and device
+# printf).  The contract is ONE JSON line on stdout: keep the real stdout aside, point fd 1 at stderr.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 # ---------------------------------------------------------------------------------------------------
 def workload_config(name: str, part_count: int = 1, part_rank: int = 0):
@@ -263,7 +272,7 @@ def run_own(args):
         out["roofline_integrate_hbm"] = hbm
     if cpu:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out))
+    emit(out)
 
 
 def stage_timings(ctx, cfg, d_frames, poses, order, stream):
@@ -421,7 +430,7 @@ def run_multi(args, rank, world, local):
             "gpu_launches": int(tracker.launches - l0), "clocks": cs.summary(),
             "e2e": None,
         }
-        print(json.dumps(out))
+        emit(out)
     dist.destroy_process_group()
 
 
@@ -456,7 +465,7 @@ def run_reference(args):
         out = dict(base, value=cpu["value"], ms_per_step=1e3 / cpu["value"], cpu_baseline=cpu,
                    e2e={"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                    note=f"reference CUDA harness unavailable ({e}); value is the CPU transliteration")
-        print(json.dumps(out))
+        emit(out)
         return
     from voxelhashing_demo_b200.scenes import pingpong
 
@@ -494,7 +503,7 @@ def run_reference(args):
                                        "(-O3 -fmad=false, no -G), its own host syncs and device printf left in; it has no CPU path"},
                cpu_port=cpu,
                e2e={"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
