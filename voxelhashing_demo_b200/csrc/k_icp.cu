@@ -235,37 +235,47 @@ __device__ __noinline__ void solveAndUpdateWarp(const float* sys, IcpState* st, 
     double dcol[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) dcol[k] = __ldcg(dev->D + k * 4 + (lane & 3));
-    float row[7];
-    const int r = lane < 6 ? lane : 0;
+#ifdef VH_ICP_TRACE
+    long long ck0 = clock64();
+#endif
+    // Gauss-Jordan on [JtJ | -Jtr], fp32, the WHOLE 6x7 system in the registers of every lane (uniform control
+    // flow: no shuffles, no divergence; r1c probe: the row-per-lane shuffle form spent 3400 cycles here).
+    // The critical path is six dependent reciprocals; everything else is independent FMUL/FADD.
+    float M[6][7];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        const int i = r < c ? r : c, j = r < c ? c : r;                         // upper-triangle index of (r, c)
-        row[c] = sys[i * 6 - (i * (i - 1)) / 2 + (j - i)];                      // selfadjointView, Solver.cpp:92
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = i; j < 6; ++j) {
+            const float a = sys[i * 6 - (i * (i - 1)) / 2 + (j - i)];          // selfadjointView, Solver.cpp:92
+            M[i][j] = a;
+            M[j][i] = a;
+        }
+        M[i][6] = -sys[21 + i];                                                // update = -(JTJinv * JTr), :110
     }
-    row[6] = -sys[21 + r];                                                     // update = -(JTJinv * JTr), :110
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        float pr[7];
+        const float inv = 1.0f / M[k][k];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) pr[c] = __shfl_sync(full, row[c], k);
-        const float inv = 1.0f / pr[k];
-        if (lane != k) {
-            const float f = row[k] * inv;
+        for (int c = k + 1; c < 7; ++c) M[k][c] *= inv;
 #pragma unroll
-            for (int c = 0; c < 7; ++c) row[c] -= f * pr[c];
+        for (int r = 0; r < 6; ++r) {
+            if (r == k) continue;
+            const float f = M[r][k];
+#pragma unroll
+            for (int c = k + 1; c < 7; ++c) M[r][c] -= f * M[k][c];
         }
     }
-    float x = 0.0f;
+    float tw[6];
+    bool ok = true;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) if (r == c) x = row[6] / row[c];
-    const bool okLane = lane >= 6 || isfinite(x);
-    if (!__all_sync(full, okLane)) {
+    for (int c = 0; c < 6; ++c) { tw[c] = M[c][6]; ok = ok && isfinite(tw[c]); }
+    if (!ok) {                                                                  // uniform: every lane holds the same values
         if (lane == 0) ctr->icpConverged = 1;
         return;
     }
-    float tw[6];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) tw[c] = __shfl_sync(full, x, c);
+#ifdef VH_ICP_TRACE
+    long long ck1 = clock64();
+#endif
     // exp([[w]x v; 0 0]) element (i, j), fp32 (ref SE3Exp, twist = (v, omega)); every lane, same A, B, C
     const float t2 = tw[3] * tw[3] + tw[4] * tw[4] + tw[5] * tw[5];
     float A, B, C;
@@ -296,6 +306,9 @@ __device__ __noinline__ void solveAndUpdateWarp(const float* sys, IcpState* st, 
         }
         uij = i == 3 ? (j == 3 ? 1.0f : 0.0f) : (j < 3 ? rot : tr);
     }
+#ifdef VH_ICP_TRACE
+    long long ck2 = clock64();
+#endif
     double pij = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -315,6 +328,14 @@ __device__ __noinline__ void solveAndUpdateWarp(const float* sys, IcpState* st, 
     }
     if (lane < 16) { dev->D[lane] = pij; st->delta[lane] = (float)pij; }
     if (lane == 0) atomicAdd(&st->iterations, 1);            // RED: nothing waits for it
+#ifdef VH_ICP_TRACE
+    if (lane == 0) {
+        long long ck3 = clock64();
+        g_icpTrace[1023 * 8 + 0] = (unsigned long long)(ck1 - ck0);
+        g_icpTrace[1023 * 8 + 1] = (unsigned long long)(ck2 - ck1);
+        g_icpTrace[1023 * 8 + 2] = (unsigned long long)(ck3 - ck2);
+    }
+#endif
 }
 
 // Tail shared by the reductions: the last CTA to arrive sums the per-CTA partials and (optionally) solves.
@@ -404,6 +425,11 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
         VH_TRACE(6);
         if (solve) solveAndUpdateWarp(sSys, st, devOf(st), v.ctr, fixedPolicy);
         VH_TRACE(7);
+#ifdef VH_ICP_TRACE_TWICE
+        // experiment: is the 2.6 us solve an instruction-cache cold miss?  run it again (same code, now hot)
+        if (solve) solveAndUpdateWarp(sSys, st, devOf(st), v.ctr, fixedPolicy);
+        VH_TRACE(5);
+#endif
     }
 }
 
