@@ -127,6 +127,17 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel_prefix: str):
+    """dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture (profiles/)."""
+    for f in sorted((ROOT / "profiles").glob("*_traffic.json"), reverse=True):
+        if f.name.startswith("r1a"):
+            continue
+        for k, v in json.loads(f.read_text()).get("bytes", {}).items():
+            if k.startswith(kernel_prefix):
+                return float(v)
+    return None
+
+
 def peaks() -> tuple[float, str]:
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -316,10 +327,12 @@ def stage_timings(ctx, cfg, d_frames, poses, order, stream):
     ach = icp_bytes / t_icp / 1e9
     integ_bytes = 16 * int(st.numUpdated) + 16 * st.numVisible + 4 * n
     roof = {"kernel": "k_icp_iter<Fixed>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": which,
-            "note": "48*W*H algorithmic bytes per launch / mean launch time over a 20-iteration Align (CUDA events); the 14.7 MB "
-                    "working set is L2-resident at VGA, so this is a fraction of the HBM peak achieved out of L2 "
-                    "(launch/latency-bound); the HBM-resident integrate roofline is under roofline_integrate_hbm",
+            "traffic": ncu_traffic("k_icp_iter"), "peak_source": which,
+            "note": "dominant kernel of the step (20 launches per frame, ~90 % of the launch list): 48*W*H algorithmic bytes per launch / "
+                    "mean launch time over a 20-iteration Align (CUDA events on the launching stream).  Its 19.7 MB working set is "
+                    "L2-resident at VGA and the launch is latency-bound (two dependent L2 round trips, grid-wide reduction, 6x6 solve: "
+                    "see DESIGN.md 3.2), so the fraction of the HBM peak is low by construction; traffic is the cold-L2 ncu capture. "
+                    "The HBM-bound kernel of the path is k_integrate: roofline_integrate_hbm",
             "integrate_c2": {"bytes": integ_bytes, "us": stages["integrate"], "GB/s": integ_bytes / (stages["integrate"] * 1e-6) / 1e9,
                              "note": "L2-resident working set: not an HBM fraction"}}
     return stages, roof
@@ -359,7 +372,8 @@ def integrate_hbm_roofline(stream):
     t = float(np.mean(times))
     ctx.close()
     return {"kernel": "k_integrate<Fixed,dense>", "bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": nbytes / t / 1e9 / peak, "traffic": None, "peak_source": which, "us": t * 1e6,
+            "frac": nbytes / t / 1e9 / peak, "traffic": ncu_traffic("k_integrate"), "algorithmic_bytes": nbytes,
+            "peak_source": which, "us": t * 1e6,
             "visible_blocks": st.numVisible, "voxel_working_set_MB": st.numVisible * 4096 / 1e6, "voxels_updated": int(st.numUpdated),
             "voxel_updates_per_s": int(st.numUpdated) / t,
             "note": "working set > 2x L2 (126 MB), 5 timed launches after 3 warm-ups, no L2 flush needed"}
