@@ -51,6 +51,14 @@ inline int f2i_rn(float x) {
     if (x <= -2147483648.0f) return kIntMin;
     return (int)std::nearbyintf(x);
 }
+// pixel rounding of the Fixed integration: nearest, ties to even, via the 1.5*2^23 trick;
+// bit-identical to nearbyintf for |u| < 2^22, far outside any image beyond that
+inline int roundPixel(float u) {
+    float t = u + 12582912.0f;
+    int32_t bits;
+    std::memcpy(&bits, &t, sizeof(bits));
+    return (int)(bits - 0x4B400000);
+}
 inline int d2i(double x) {
     if (std::isnan(x)) return 0;
     if (x >= 2147483648.0) return kIntMax;
@@ -605,7 +613,7 @@ static long long integrateImpl(vo_table* t, const float* pose, const float* dept
                         if (!(pcz > 0.0f)) continue;
                         float iz = 1.0f / pcz;
                         float u = fmaf(pcx * iz, fx, cx), v = fmaf(pcy * iz, fy, cy);
-                        int px = f2i_rn(u), py = f2i_rn(v);                    // nearest pixel, ties to even
+                        int px = roundPixel(u), py = roundPixel(v);            // nearest pixel, ties to even
                         if ((unsigned)px >= (unsigned)W || (unsigned)py >= (unsigned)H) continue;
                         float d = depthSrc[(size_t)(py * W + px) * stride + zoff];
                         if (!(d > c.depthMin && d < c.depthMax)) continue;

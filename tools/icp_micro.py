@@ -56,6 +56,7 @@ print("  reduce 8 rows           :", graph_time(lambda: ctx.icp_reduce(b[0], b[1
 print("  solve only              :", graph_time(lambda: ctx.icp_solve(sysbuf, s)))
 ctx.icp_reset(True, s)
 print("  iterate (reduce+solve)  :", graph_time(lambda: ctx.icp_iterate(b[0], b[1], a[0], a[1], s)))
+print("  align x20 (PDL chain)/20:", graph_time(lambda: ctx.icp_align(b[0], b[1], a[0], a[1], 20, s), 1) / 20)
 print("  set_pose                :", graph_time(lambda: ctx.set_pose(np.eye(4, dtype=np.float32), s)))
 print("  preprocess              :", graph_time(lambda: ctx.preprocess(d[0], *a, s)))
 print("  alloc                   :", graph_time(lambda: ctx.alloc_blocks(a[0], a[1], s)))

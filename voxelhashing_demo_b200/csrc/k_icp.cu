@@ -446,10 +446,12 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_iter(View v, IcpState* s
     const int begin = row0 * v.W, end = row1 * v.W;
     const int T = gridDim.x * blockDim.x;
     int i0 = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    // the flag, delta and the first batch of source vertices are independent loads: issue them together
-    const int conv = first ? 0 : v.ctr->icpConverged;
-    float dl = 0.f;
-    if (threadIdx.x < 16) dl = st->delta[threadIdx.x];
+    // Programmatic dependent launch (iterations 2..n of an Align are launched with the PDL attribute): let the
+    // NEXT iteration's CTAs be scheduled as soon as this grid's CTAs retire, and do everything that does not
+    // depend on the previous iteration -- the launch itself and the first batch of source loads (the input
+    // vertex map is constant during an Align) -- while the previous grid's last CTA is still reducing and
+    // solving.  griddepcontrol.wait then blocks until that grid has completed and flushed (delta, flag, ticket).
+    asm volatile("griddepcontrol.launch_dependents;");
     float4 s[B];
 #pragma unroll
     for (int j = 0; j < B; ++j) {
@@ -457,6 +459,11 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_iter(View v, IcpState* s
         s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (idx < end) s[j] = __ldg(in + idx);
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the flag and delta are independent loads: issue them together
+    const int conv = first ? 0 : __ldcg(&v.ctr->icpConverged);
+    float dl = 0.f;
+    if (threadIdx.x < 16) dl = __ldcg(st->delta + threadIdx.x);
     if (conv) return;                                       // uniform over the grid: the flag only changes in a tail
     if (threadIdx.x < 16) sDelta[threadIdx.x] = dl;
     __syncthreads();
@@ -651,32 +658,48 @@ static int icpGrid(const vh_context* c, int pixels, int threads, int perSM) {
     return g < 1 ? 1 : g;
 }
 
+// One CTA per SM (VGA = 4.1 pixels per thread, one trip of <= 5).  Iterations after the first of an Align are
+// programmatic dependent launches on numSMs - 1 CTAs, so the whole next grid can become resident next to the
+// previous grid's last CTA (which still owns one SM's register file while it reduces and solves).
+static cudaError_t launchIcp(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN, int row0,
+                             int row1, vh_icp_system* d_out, bool solve, bool first, bool chained, const PeerView& pv, cudaStream_t s) {
+    // chained: the previous launch on this stream is the previous iteration of the SAME Align (same input maps)
+    const bool pdl = chained && !first && c->numSMs > 2;
+    int g = icpGrid(c, (row1 - row0) * c->v.W, kIcpThreads, 1);
+    if (g >= c->numSMs) g = c->numSMs - 1;                  // same grid for every iteration: same summation order
+    if (g < 1) g = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)g);
+    cfg.blockDim = dim3(kIcpThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const int solveI = solve ? 1 : 0, firstI = first ? 1 : 0;
+    if (c->cfg.policy == VH_POLICY_FIXED)
+        return cudaLaunchKernelEx(&cfg, k_icp_iter<Fixed>, c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solveI, firstI, pv);
+    return cudaLaunchKernelEx(&cfg, k_icp_iter<RefExact>, c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solveI, firstI, pv);
+}
+
 cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                             int row0, int row1, vh_icp_system* d_out, bool solve, cudaStream_t s) {
-    return launch_icp_iter_ex(c, in, inN, tg, tgN, row0, row1, d_out, solve, false, s);
+    return launch_icp_iter_ex(c, in, inN, tg, tgN, row0, row1, d_out, solve, false, false, s);
 }
 
 cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
-                               int row0, int row1, vh_icp_system* d_out, bool solve, bool first, cudaStream_t s) {
-    int g = icpGrid(c, (row1 - row0) * c->v.W, kIcpThreads, 1);               // one CTA per SM; VGA = 4.05 pixels per thread, one trip of <= 5
+                               int row0, int row1, vh_icp_system* d_out, bool solve, bool first, bool chained, cudaStream_t s) {
     PeerView none{};
     none.world = 1;
-    if (c->cfg.policy == VH_POLICY_FIXED)
-        k_icp_iter<Fixed><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first, none);
-    else
-        k_icp_iter<RefExact><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, d_out, solve, first, none);
-    return cudaGetLastError();
+    return launchIcp(c, in, inN, tg, tgN, row0, row1, d_out, solve, first, chained, none, s);
 }
 
 // One iteration over this rank's image rows with the all-reduce fused into the kernel's epilogue.
 cudaError_t launch_icp_iter_peer(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                  int row0, int row1, bool first, cudaStream_t s) {
-    int g = icpGrid(c, (row1 - row0) * c->v.W, kIcpThreads, 1);
-    if (c->cfg.policy == VH_POLICY_FIXED)
-        k_icp_iter<Fixed><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, nullptr, 1, first, c->peers);
-    else
-        k_icp_iter<RefExact><<<g, kIcpThreads, 0, s>>>(c->v, c->icp, c->icpPartials, in, inN, tg, tgN, row0, row1, nullptr, 1, first, c->peers);
-    return cudaGetLastError();
+    return launchIcp(c, in, inN, tg, tgN, row0, row1, nullptr, true, first, !first, c->peers, s);
 }
 
 cudaError_t launch_icp_solve(vh_context* c, const vh_icp_system* d_sys, cudaStream_t s) {

@@ -281,7 +281,7 @@ int vh_icp_reset(vh_context* c, int reset_estimate, vh_stream s) {
 }
 int vh_icp_iterate(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN, vh_stream s) {
     if (!c || !in || !tg || !tgN) return fail(VH_ERR_INVALID, "vh_icp_iterate: null argument");
-    VH_CUDA(launch_icp_iter_ex(c, in, inN, tg, tgN, 0, c->v.H, nullptr, true, false, S(s)));
+    VH_CUDA(launch_icp_iter_ex(c, in, inN, tg, tgN, 0, c->v.H, nullptr, true, false, false, S(s)));
     return VH_OK;
 }
 int vh_icp_align(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN, int iterations,
@@ -289,14 +289,14 @@ int vh_icp_align(vh_context* c, const float4* in, const float4* inN, const float
     if (!c || !in || !tg || !tgN) return fail(VH_ERR_INVALID, "vh_icp_align: null argument");
     if (iterations <= 0) iterations = c->cfg.icpIterations;
     for (int it = 0; it < iterations; ++it)                      // CameraTracking.cpp:35
-        VH_CUDA(launch_icp_iter_ex(c, in, inN, tg, tgN, 0, c->v.H, nullptr, true, it == 0, S(s)));
+        VH_CUDA(launch_icp_iter_ex(c, in, inN, tg, tgN, 0, c->v.H, nullptr, true, it == 0, it > 0, S(s)));
     return VH_OK;
 }
 int vh_icp_reduce(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN, int row0, int row1,
                   vh_icp_system* d_system, vh_stream s) {
     if (!c || !in || !tg || !tgN || !d_system) return fail(VH_ERR_INVALID, "vh_icp_reduce: null argument");
     if (row0 < 0 || row1 > c->v.H || row0 > row1) return fail(VH_ERR_INVALID, "vh_icp_reduce: bad row range");
-    VH_CUDA(launch_icp_iter_ex(c, in, inN, tg, tgN, row0, row1, d_system, false, true, S(s)));
+    VH_CUDA(launch_icp_iter_ex(c, in, inN, tg, tgN, row0, row1, d_system, false, true, false, S(s)));
     return VH_OK;
 }
 // Multi-GPU: peer-mapped exchange regions (one per rank, VH_PEER_BYTES each, zero-initialised), e.g. from

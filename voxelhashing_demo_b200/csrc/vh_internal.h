@@ -115,7 +115,7 @@ cudaError_t launch_preprocess(vh_context* c, const uint16_t* depth, float4* vert
 cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                             int row0, int row1, vh_icp_system* d_out, bool solve, cudaStream_t s);
 cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
-                               int row0, int row1, vh_icp_system* d_out, bool solve, bool first, cudaStream_t s);
+                               int row0, int row1, vh_icp_system* d_out, bool solve, bool first, bool chained, cudaStream_t s);
 cudaError_t launch_icp_solve(vh_context* c, const vh_icp_system* d_sys, cudaStream_t s);
 cudaError_t launch_icp_iter_peer(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                  int row0, int row1, bool first, cudaStream_t s);

@@ -23,7 +23,10 @@ struct vh_pipeline {
     long long frame;
     long long launches;
     float* d_pose;                 // camera -> world of the latest frame, row-major
-    uint16_t* d_depthStage;        // H2D landing buffer of push_host
+    uint16_t* d_depthStage[2];     // H2D landing buffers of push_host (double-buffered)
+    cudaStream_t copyStream;       // H2D of frame k+1 overlaps the compute of frame k
+    cudaEvent_t evCopied[2], evConsumed[2];
+    long long hostFrames;
     float4* verts[2];
     float4* normals[2];
     float* depthf[2];
@@ -55,7 +58,7 @@ cudaError_t enqueueBody(vh_pipeline* p, int par, bool track, cudaStream_t s, int
         const float4* tg = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelVerts : p->verts[1 - par];
         const float4* tgN = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelNormals : p->normals[1 - par];
         for (int it = 0; it < p->iterations; ++it) {                       // CameraTracking.cpp:35
-            e = launch_icp_iter_ex(c, in, inN, tg, tgN, 0, c->v.H, nullptr, true, it == 0, s);
+            e = launch_icp_iter_ex(c, in, inN, tg, tgN, 0, c->v.H, nullptr, true, it == 0, it > 0, s);
             if (e != cudaSuccess) return e;
             ++k;
         }
@@ -99,11 +102,14 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     chk(cudaMalloc((void**)&p->d_pose, 16 * sizeof(float)));
-    chk(cudaMalloc((void**)&p->d_depthStage, px * sizeof(uint16_t)));
+    chk(cudaStreamCreateWithFlags(&p->copyStream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         chk(cudaMalloc((void**)&p->verts[i], px * sizeof(float4)));
         chk(cudaMalloc((void**)&p->normals[i], px * sizeof(float4)));
         chk(cudaMalloc((void**)&p->depthf[i], px * sizeof(float)));
+        chk(cudaMalloc((void**)&p->d_depthStage[i], px * sizeof(uint16_t)));
+        chk(cudaEventCreateWithFlags(&p->evCopied[i], cudaEventDisableTiming));
+        chk(cudaEventCreateWithFlags(&p->evConsumed[i], cudaEventDisableTiming));
     }
     if (mode == VH_TRACK_FRAME_TO_MODEL) {
         chk(cudaMalloc((void**)&p->modelVerts, px * sizeof(float4)));
@@ -120,9 +126,12 @@ void vh_pipeline_destroy(vh_pipeline* p) {
     if (!p) return;
     for (int i = 0; i < 2; ++i) {
         if (p->haveGraph[i]) { cudaGraphExecDestroy(p->exec[i]); cudaGraphDestroy(p->graph[i]); }
-        cudaFree(p->verts[i]); cudaFree(p->normals[i]); cudaFree(p->depthf[i]);
+        cudaFree(p->verts[i]); cudaFree(p->normals[i]); cudaFree(p->depthf[i]); cudaFree(p->d_depthStage[i]);
+        if (p->evCopied[i]) cudaEventDestroy(p->evCopied[i]);
+        if (p->evConsumed[i]) cudaEventDestroy(p->evConsumed[i]);
     }
-    cudaFree(p->modelVerts); cudaFree(p->modelNormals); cudaFree(p->d_pose); cudaFree(p->d_depthStage);
+    if (p->copyStream) cudaStreamDestroy(p->copyStream);
+    cudaFree(p->modelVerts); cudaFree(p->modelNormals); cudaFree(p->d_pose);
     delete p;
 }
 
@@ -138,12 +147,11 @@ int vh_pipeline_reset(vh_pipeline* p, const float* pose16_host, vh_stream s) {
     return VH_OK;
 }
 
-int vh_pipeline_push_device(vh_pipeline* p, const uint16_t* d_depth, vh_stream s) {
-    if (!p || !d_depth) return pfail(VH_ERR_INVALID, "vh_pipeline_push_device: null argument");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, cudaEvent_t afterPreprocess) {
     vh_context* c = p->ctx;
     const int par = (int)(p->frame & 1);
     PCUDA(launch_preprocess(c, d_depth, p->verts[par], p->normals[par], p->depthf[par], st));   // Application.cpp:73
+    if (afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, st));      // the raw depth buffer may be overwritten from here on
     p->launches += 1;
     const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
     int n = 0;
@@ -173,13 +181,25 @@ int vh_pipeline_push_device(vh_pipeline* p, const uint16_t* d_depth, vh_stream s
     return VH_OK;
 }
 
+int vh_pipeline_push_device(vh_pipeline* p, const uint16_t* d_depth, vh_stream s) {
+    if (!p || !d_depth) return pfail(VH_ERR_INVALID, "vh_pipeline_push_device: null argument");
+    return pushFrame(p, d_depth, reinterpret_cast<cudaStream_t>(s), nullptr);
+}
+
 // e2e entry: depth in (pinned) host memory, pose back to host memory; returns after enqueueing.
+// The H2D copy runs on the pipeline's own copy stream into one of two staging buffers, so the copy of frame
+// k+1 overlaps the compute of frame k; events order copy -> preprocess and preprocess -> reuse of the buffer.
 int vh_pipeline_push_host(vh_pipeline* p, const uint16_t* h_depth, float* h_pose_out16, vh_stream s) {
     if (!p || !h_depth) return pfail(VH_ERR_INVALID, "vh_pipeline_push_host: null argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
     const size_t bytes = (size_t)p->ctx->v.W * p->ctx->v.H * sizeof(uint16_t);
-    PCUDA(cudaMemcpyAsync(p->d_depthStage, h_depth, bytes, cudaMemcpyHostToDevice, st));
-    int rc = vh_pipeline_push_device(p, p->d_depthStage, s);
+    const int slot = (int)(p->hostFrames & 1);
+    if (p->hostFrames >= 2) PCUDA(cudaStreamWaitEvent(p->copyStream, p->evConsumed[slot], 0));
+    PCUDA(cudaMemcpyAsync(p->d_depthStage[slot], h_depth, bytes, cudaMemcpyHostToDevice, p->copyStream));
+    PCUDA(cudaEventRecord(p->evCopied[slot], p->copyStream));
+    PCUDA(cudaStreamWaitEvent(st, p->evCopied[slot], 0));
+    p->hostFrames += 1;
+    int rc = pushFrame(p, p->d_depthStage[slot], st, p->evConsumed[slot]);
     if (rc != VH_OK) return rc;
     if (h_pose_out16) PCUDA(cudaMemcpyAsync(h_pose_out16, p->d_pose, 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return VH_OK;
