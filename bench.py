@@ -427,6 +427,21 @@ def run_multi(args, rank, world, local):
     counts = torch.tensor([float(st.numUpdated), float(st.numVisible), float(st.numAllocated)], device="cuda")
     dist.all_reduce(counts)
     pose = tracker.pose()
+    # integration alone on this rank's partition (the stage that shards): max over ranks of the device time
+    df = tracker.maps[(tracker.frame - 1) & 1][2]
+    t_int = []
+    for i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.integrate_depthf(df)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if i >= 2:
+            t_int.append(e0.elapsed_time(e1))
+    t_int = torch.tensor([float(np.mean(t_int))], device="cuda")
+    dist.all_reduce(t_int, op=dist.ReduceOp.MAX)
+    upd = torch.tensor([float(ctx.stats().numUpdated)], device="cuda")
+    dist.all_reduce(upd)
     if rank == 0:
         ms = float(ms.item())
         truth = poses[order[-1]]
@@ -441,6 +456,9 @@ def run_multi(args, rank, world, local):
                        "final_pose_translation_error_m": float(np.max(np.abs(pose[:3, 3] - truth[:3, 3]))),
                        "visible_blocks_all_ranks": int(counts[1].item()), "allocated_blocks_all_ranks": int(counts[2].item())},
             "voxel_updates_per_s": float(counts[0].item()) / (ms / K / 1e3),
+            "integrate_stage": {"us_max_over_ranks": float(t_int.item()) * 1e3, "voxels_updated_all_ranks": int(upd.item()),
+                                "voxel_updates_per_s": float(upd.item()) / (float(t_int.item()) * 1e-3),
+                                "note": "k_integrate alone on each rank's partition of the hash space; the stage that shards"},
             "gpu_launches": int(tracker.launches - l0), "clocks": cs.summary(),
             "e2e": None,
         }
