@@ -402,6 +402,26 @@ def run_multi(args, rank, world, local):
     else:
         poses = [traj(k) for k in range(n_unique)]
         d_frames = None
+    # the same workload on ONE GPU (rank 0, unpartitioned), so the strong-scaling factor can be read off one line
+    single = None
+    if rank == 0 and not args.no_single:
+        cfg1, _, _, _ = workload_config(name, 1, 0)
+        ctx1 = Context(cfg1)
+        t1 = PartitionedTracker(ctx1, 0, 1)
+        t1.reset(poses[order[0]].astype(np.float32))
+        for i in range(W):
+            t1.push(d_frames[order[i]])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(W, W + K):
+            t1.push(d_frames[order[i]])
+        e1.record()
+        torch.cuda.synchronize()
+        single = {"value": K / (e0.elapsed_time(e1) / 1e3), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / K, "n_gpus": 1}
+        del t1
+        ctx1.close()
+    dist.barrier()
     ctx = Context(cfg)
     tracker = PartitionedTracker(ctx, rank, world)
     stream = torch.cuda.current_stream()
@@ -427,6 +447,20 @@ def run_multi(args, rank, world, local):
     counts = torch.tensor([float(st.numUpdated), float(st.numVisible), float(st.numAllocated)], device="cuda")
     dist.all_reduce(counts)
     pose = tracker.pose()
+    # end to end: the ingest rank holds the frames in pinned HOST memory; every step copies one frame H2D, the
+    # frame is broadcast, and every rank reads its pose back D2H
+    h_frames = torch.from_numpy(frames).pin_memory() if rank == 0 else None
+    h_pose = torch.zeros((K, 16), dtype=torch.float32).pin_memory()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for i in range(W, W + K):
+        tracker.push(h_frames[order[i]] if rank == 0 else None)
+        h_pose[i - W].copy_(tracker.d_pose, non_blocking=True)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms_e2e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     # integration alone on this rank's partition (the stage that shards): max over ranks of the device time
     df = tracker.maps[(tracker.frame - 1) & 1][2]
     t_int = []
@@ -460,7 +494,9 @@ def run_multi(args, rank, world, local):
                                 "voxel_updates_per_s": float(upd.item()) / (float(t_int.item()) * 1e-3),
                                 "note": "k_integrate alone on each rank's partition of the hash space; the stage that shards"},
             "gpu_launches": int(tracker.launches - l0), "clocks": cs.summary(),
-            "e2e": None,
+            "single_gpu_same_workload": single,
+            "e2e": {"value": K / (float(ms_e2e.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(cfg.width * cfg.height * 2),
+                    "d2h_bytes_per_step": 64 * world, "ms_per_step": float(ms_e2e.item()) / K},
         }
         emit(out)
     dist.destroy_process_group()
@@ -547,6 +583,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "C2", "C3", "C4"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm", action="store_true", help="skip the large-volume integrate roofline leg")
+    ap.add_argument("--no-single", action="store_true", help="multi-GPU: skip the 1-GPU run of the same workload")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -88,10 +88,11 @@ class PartitionedTracker:
         self.frame = 0
 
     def push(self, d_depth=None):
-        """One frame.  Rank 0 passes the device depth image; the others pass None."""
+        """One frame.  Rank 0 passes the depth image (device tensor, or pinned host tensor for the end-to-end
+        path); the others pass None."""
         ctx, dist = self.ctx, self.dist
         if self.rank == 0:
-            self.depth.copy_(d_depth.view(self.depth.dtype))
+            self.depth.copy_(d_depth.view(self.depth.dtype), non_blocking=True)    # device or pinned host source
         if self.world > 1:
             dist.broadcast(self.depth.view(self.torch.uint8), src=0, group=self.group)   # raw bytes over NVLink / NVSwitch
         par = self.frame & 1
