@@ -52,7 +52,7 @@ def emit(obj) -> None:
 def workload_config(name: str, part_count: int = 1, part_rank: int = 0):
     from voxelhashing_demo_b200 import POLICY_FIXED, Config, scenes
 
-    if name == "C2":
+    if name in ("C2", "C5"):
         cfg = Config(policy=POLICY_FIXED, numBuckets=100003, bucketSize=5, numVoxelBlocks=65536, voxelSize=0.02,
                      truncation=0.06, truncScale=0.01, overflowSlots=16384, icpNormalThres=0.8, icpIterations=20,
                      partCount=part_count, partRank=part_rank)
@@ -230,7 +230,8 @@ def run_own(args):
 
     def run_sequence(host: bool):
         ctx.reset(stream)
-        pipe = FramePipeline(ctx, iterations=cfg.icpIterations, mode=FramePipeline.FRAME_TO_FRAME, use_graph=True)
+        mode = FramePipeline.FRAME_TO_MODEL if name == "C5" else FramePipeline.FRAME_TO_FRAME
+        pipe = FramePipeline(ctx, iterations=cfg.icpIterations, mode=mode, use_graph=True)
         with torch.cuda.stream(stream):
             pipe.reset(poses[order[0]].astype(np.float32), stream)
             for i in range(W):
@@ -264,7 +265,7 @@ def run_own(args):
         "metric": METRIC, "value": K / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: {n_unique}-frame synthetic {cfg.width}x{cfg.height} sequence (scene S1T, trajectory C2), "
+        "config": {"workload": f"{name}: {n_unique}-frame synthetic {cfg.width}x{cfg.height} sequence ({'frame-to-MODEL tracking, raycast in the loop; ' if name == 'C5' else ''}analytic scene, known trajectory), "
                                f"voxel {cfg.voxelSize} m, {cfg.numBuckets}x{cfg.bucketSize} buckets, {cfg.numVoxelBlocks} blocks, "
                                f"ICP {cfg.icpIterations} iterations x 1 level, Fixed policy",
                    "l2": f"inputs larger than L2: {n_unique} distinct u16 frames = {n_unique * frame_bytes / 1e6:.0f} MB cycled; the visible "
@@ -580,7 +581,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default=None, choices=[None, "C2", "C3", "C4"])
+    ap.add_argument("--workload", default=None, choices=[None, "C2", "C3", "C4", "C5"],
+                    help="C2 (default at N=1), C3 (720p, 5 mm), C4 (large volume; default at N>1), C5 (C2 tracked frame-to-model: raycast in the loop)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm", action="store_true", help="skip the large-volume integrate roofline leg")
     ap.add_argument("--no-single", action="store_true", help="multi-GPU: skip the 1-GPU run of the same workload")

@@ -976,6 +976,39 @@ void vo_raycast(vo_table* t, const float* pose, float* verts, float* normals) {
     const int W = c.width, H = c.height;
     const float vs = c.voxelSize, invVs = 1.0f / vs;
     const float coarse = 4.0f * vs;
+    // ray intervals from the visible blocks of THIS pose: 1/8-resolution min / max depth of the block corners
+    vo_compact(t, pose);
+    const int TS = 8, tw = (W + TS - 1) / TS, th = (H + TS - 1) / TS;
+    std::vector<float> tileMin((size_t)tw * th, 3.3895314e38f), tileMax((size_t)tw * th, 0.0f);   // 0x7f7f7f7f, 0
+    {
+        float inv[16];
+        mat4_inverse(pose, inv);
+        const float fx = c.K[0], fy = c.K[4], cx = c.K[2], cy = c.K[5];
+        for (const Entry& e : t->compact) {
+            float umin = INFINITY, umax = -INFINITY, wmin = INFINITY, wmax = -INFINITY, zmin = INFINITY, zmax = -INFINITY;
+            for (int k = 0; k < 8; ++k) {
+                float wx = ((float)(e.pos.x * 8 + ((k & 1) ? 8 : 0)) - 0.5f) * vs;
+                float wy = ((float)(e.pos.y * 8 + ((k & 2) ? 8 : 0)) - 0.5f) * vs;
+                float wz = ((float)(e.pos.z * 8 + ((k & 4) ? 8 : 0)) - 0.5f) * vs;
+                V4 p = mul4(inv, V4{wx, wy, wz, 1.0f});
+                float zc = fmaxf(p.z, 0.05f);
+                float u = p.x / zc * fx + cx, w = p.y / zc * fy + cy;
+                umin = fminf(umin, u); umax = fmaxf(umax, u);
+                wmin = fminf(wmin, w); wmax = fmaxf(wmax, w);
+                zmin = fminf(zmin, p.z); zmax = fmaxf(zmax, p.z);
+            }
+            if (!(zmax > 0.0f)) continue;
+            int x0 = std::min(std::max(f2i(floorf(umin)) - 1, 0), W - 1) / TS, x1 = std::min(std::max(f2i(floorf(umax)) + 2, 0), W - 1) / TS;
+            int y0 = std::min(std::max(f2i(floorf(wmin)) - 1, 0), H - 1) / TS, y1 = std::min(std::max(f2i(floorf(wmax)) + 2, 0), H - 1) / TS;
+            if (umax < -1.0f || wmax < -1.0f || umin > (float)W || wmin > (float)H) continue;
+            float lo = fmaxf(zmin, c.depthMin);
+            for (int ty = y0; ty <= y1; ++ty)
+                for (int tx = x0; tx <= x1; ++tx) {
+                    tileMin[(size_t)ty * tw + tx] = fminf(tileMin[(size_t)ty * tw + tx], lo);
+                    tileMax[(size_t)ty * tw + tx] = fmaxf(tileMax[(size_t)ty * tw + tx], zmax);
+                }
+        }
+    }
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
@@ -991,10 +1024,12 @@ void vo_raycast(vo_table* t, const float* pose, float* verts, float* normals) {
             float dwz = pose[8] * rd.x + pose[9] * rd.y + pose[10] * rd.z;
             const float ox = pose[3], oy = pose[7], oz = pose[11];
             BlockCache bc{I3{0, 0, 0}, nullptr, false};
-            float z = c.depthMin, zPrev = 0, sPrev = 0;
+            const float tmin = tileMin[(size_t)(y / TS) * tw + (x / TS)], tmax = tileMax[(size_t)(y / TS) * tw + (x / TS)];
+            float z = fmaxf(c.depthMin, tmin - vs), zPrev = 0, sPrev = 0;
+            const float zEnd = (tmin <= tmax) ? fminf(c.depthMax, tmax + vs) : 0.0f;
             bool havePrev = false, hit = false;
             float zHit = 0;
-            for (int it = 0; it < 4096 && z < c.depthMax; ++it) {
+            for (int it = 0; it < 4096 && z < zEnd; ++it) {
                 float px = fmaf(z, dwx, ox), py = fmaf(z, dwy, oy), pz = fmaf(z, dwz, oz);
                 float s;
                 if (sampleTrilinear(t, bc, px, py, pz, invVs, s)) {

@@ -44,7 +44,48 @@ __device__ __forceinline__ bool sampleTrilinear(const View& v, BlockCache& bc, f
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_raycast(View v, float4* __restrict__ verts, float4* __restrict__ normals) {
+// Ray intervals (what the reference's depthWrite.* pass was meant to produce, notes.md:9-16): every visible
+// block splats the depth range of its eight corners into a 1/8-resolution min / max image (positive floats
+// order like their bit patterns, so atomicMin / atomicMax on ints), and a ray only marches [min - vs, max + vs]
+// of its tile instead of the whole sensor range.
+constexpr int kTile = 8;
+
+__global__ void __launch_bounds__(128) k_ray_interval(View v, int* __restrict__ tileMin, int* __restrict__ tileMax) {
+    __shared__ float sInv[16];
+    if (threadIdx.x < 16) sInv[threadIdx.x] = v.frame->inv[threadIdx.x];
+    __syncthreads();
+    const int count = v.ctr->compactCount;
+    const int tw = (v.W + kTile - 1) / kTile;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < count; b += gridDim.x * blockDim.x) {
+        const int4 e = __ldg(v.compact16 + b);
+        float umin = INFINITY, umax = -INFINITY, wmin = INFINITY, wmax = -INFINITY, zmin = INFINITY, zmax = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float wx = ((float)(e.x * 8 + ((k & 1) ? 8 : 0)) - 0.5f) * v.voxelSize;
+            const float wy = ((float)(e.y * 8 + ((k & 2) ? 8 : 0)) - 0.5f) * v.voxelSize;
+            const float wz = ((float)(e.z * 8 + ((k & 4) ? 8 : 0)) - 0.5f) * v.voxelSize;
+            const float4 p = mul4(sInv, wx, wy, wz, 1.0f);
+            const float zc = fmaxf(p.z, 0.05f);
+            const float u = p.x / zc * v.fx + v.cx, w = p.y / zc * v.fy + v.cy;
+            umin = fminf(umin, u); umax = fmaxf(umax, u);
+            wmin = fminf(wmin, w); wmax = fmaxf(wmax, w);
+            zmin = fminf(zmin, p.z); zmax = fmaxf(zmax, p.z);
+        }
+        if (!(zmax > 0.0f)) continue;
+        const int x0 = min(max(f2i(floorf(umin)) - 1, 0), v.W - 1) / kTile, x1 = min(max(f2i(floorf(umax)) + 2, 0), v.W - 1) / kTile;
+        const int y0 = min(max(f2i(floorf(wmin)) - 1, 0), v.H - 1) / kTile, y1 = min(max(f2i(floorf(wmax)) + 2, 0), v.H - 1) / kTile;
+        if (umax < -1.0f || wmax < -1.0f || umin > (float)v.W || wmin > (float)v.H) continue;
+        const int lo = __float_as_int(fmaxf(zmin, v.depthMin)), hi = __float_as_int(zmax);
+        for (int ty = y0; ty <= y1; ++ty)
+            for (int tx = x0; tx <= x1; ++tx) {
+                atomicMin(tileMin + ty * tw + tx, lo);
+                atomicMax(tileMax + ty * tw + tx, hi);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_raycast(View v, const int* __restrict__ tileMin, const int* __restrict__ tileMax,
+                                                 float4* __restrict__ verts, float4* __restrict__ normals) {
     __shared__ float sPose[16];
     if (threadIdx.x < 16) sPose[threadIdx.x] = v.frame->pose[threadIdx.x];
     __syncthreads();
@@ -60,9 +101,12 @@ __global__ void __launch_bounds__(128) k_raycast(View v, float4* __restrict__ ve
     const float dwz = sPose[8] * rd.x + sPose[9] * rd.y + sPose[10] * rd.z;
     const float ox = sPose[3], oy = sPose[7], oz = sPose[11];
     BlockCache bc{0, 0, 0, nullptr, false};
-    float z = v.depthMin, zPrev = 0.f, sPrev = 0.f, zHit = 0.f;
+    const int tile = (y / kTile) * ((v.W + kTile - 1) / kTile) + (x / kTile);
+    const float tmin = __int_as_float(__ldg(tileMin + tile)), tmax = __int_as_float(__ldg(tileMax + tile));
+    float z = fmaxf(v.depthMin, tmin - vs), zPrev = 0.f, sPrev = 0.f, zHit = 0.f;
+    const float zEnd = (tmin <= tmax) ? fminf(v.depthMax, tmax + vs) : 0.0f;     // empty tile: no visible block on this ray
     bool havePrev = false, hit = false;
-    for (int it = 0; it < 4096 && z < v.depthMax; ++it) {
+    for (int it = 0; it < 4096 && z < zEnd; ++it) {
         const float px = fmaf(z, dwx, ox), py = fmaf(z, dwy, oy), pz = fmaf(z, dwz, oz);
         float s;
         if (sampleTrilinear(v, bc, px, py, pz, s)) {
@@ -103,9 +147,18 @@ __global__ void __launch_bounds__(128) k_raycast(View v, float4* __restrict__ ve
     normals[idx] = no;
 }
 
+// Needs the visible list of the CURRENT pose (vh_raycast refreshes it; the frame pipeline has just built it).
 cudaError_t launch_raycast(vh_context* c, float4* verts, float4* normals, cudaStream_t s) {
+    const int tiles = ((c->v.W + kTile - 1) / kTile) * ((c->v.H + kTile - 1) / kTile);
+    cudaError_t e = cudaMemsetAsync(c->tileMin, 0x7f, sizeof(int) * tiles, s);       // 0x7f7f7f7f = 3.4e38
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(c->tileMax, 0, sizeof(int) * tiles, s);
+    if (e != cudaSuccess) return e;
+    k_ray_interval<<<c->numSMs, 128, 0, s>>>(c->v, c->tileMin, c->tileMax);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     dim3 grid((c->v.W + 15) / 16, (c->v.H + 7) / 8);
-    k_raycast<<<grid, 128, 0, s>>>(c->v, verts, normals);
+    k_raycast<<<grid, 128, 0, s>>>(c->v, c->tileMin, c->tileMax, verts, normals);
     return cudaGetLastError();
 }
 

@@ -155,6 +155,11 @@ int vh_create(const vh_config* cfg, vh_context** out) {
         c->icp = static_cast<IcpState*>(p);
     }
     chk(devAlloc(c, &c->icpPartials, (size_t)kIcpMaxBlocks * 32));
+    {
+        const size_t tiles = (size_t)((cfg->width + 7) / 8) * ((cfg->height + 7) / 8);
+        chk(devAlloc(c, &c->tileMin, tiles));
+        chk(devAlloc(c, &c->tileMax, tiles));
+    }
     if (e != cudaSuccess) { vh_destroy(c); return fail(VH_ERR_CUDA, "vh_create: cudaMalloc", e); }
     v.frame = c->frame;
     float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -172,7 +177,7 @@ void vh_destroy(vh_context* c) {
     if (!c) return;
     cudaFree(c->v.entries); cudaFree(c->v.chain); cudaFree(c->v.mutex); cudaFree(c->v.heap);
     cudaFree(c->v.blockInfo); cudaFree(c->v.voxels); cudaFree(c->v.compact16); cudaFree(c->v.compact20);
-    cudaFree(c->v.ctr); cudaFree(c->frame); cudaFree(c->icp); cudaFree(c->icpPartials);
+    cudaFree(c->v.ctr); cudaFree(c->frame); cudaFree(c->icp); cudaFree(c->icpPartials); cudaFree(c->tileMin); cudaFree(c->tileMax);
     delete c;
 }
 
@@ -370,6 +375,8 @@ int vh_jacobians(vh_context* c, const float4* corr, const float4* corrN, float* 
 int vh_raycast(vh_context* c, float4* d_verts, float4* d_normals, vh_stream s) {
     if (!c || !d_verts || !d_normals) return fail(VH_ERR_INVALID, "vh_raycast: null argument");
     if (c->cfg.policy != VH_POLICY_FIXED) return fail(VH_ERR_INVALID, "vh_raycast: Fixed policy only (the RefExact TSDF is not a surface)");
+    VH_CUDA(cudaMemsetAsync(&c->v.ctr->compactCount, 0, sizeof(int), S(s)));
+    VH_CUDA(launch_compact(c, S(s)));                    // the visible list of the CURRENT pose feeds the ray intervals
     VH_CUDA(launch_raycast(c, d_verts, d_normals, S(s)));
     return VH_OK;
 }

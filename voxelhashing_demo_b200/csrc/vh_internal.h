@@ -94,6 +94,8 @@ struct vh_context {
     vh::FrameParams* frame;
     vh::IcpState* icp;
     float* icpPartials;       // kIcpMaxBlocks x 32
+    int* tileMin;             // raycast ray intervals, (W/8) x (H/8), float bit patterns
+    int* tileMax;
     int numSMs;
     size_t bytesAllocated;
     // host-visible copy of the RefExact fusion-side projection flag etc.
