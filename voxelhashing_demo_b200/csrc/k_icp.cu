@@ -394,7 +394,8 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
     __syncthreads();
     VH_TRACE(4);
     if (!isLast) return;
-    __threadfence();
+    // No second fence: every writer fenced before its ticket, this CTA's ticket came after all of them, and the
+    // loads below bypass L1 (ld.cg), so they observe the rows in L2 (the threadFenceReduction pattern).
     {
         const unsigned c4 = threadIdx.x & 7, r0 = threadIdx.x >> 3, R = blockDim.x >> 3;
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -403,14 +404,23 @@ __device__ void reduceTail(const View& v, IcpState* st, float* partials, float t
             const float4 p = __ldcg(reinterpret_cast<const float4*>(partials + (size_t)b * 32) + c4);
             a0 += (double)p.x; a1 += (double)p.y; a2 += (double)p.z; a3 += (double)p.w;
         }
-        sRows[r0][c4 * 4 + 0] = a0; sRows[r0][c4 * 4 + 1] = a1; sRows[r0][c4 * 4 + 2] = a2; sRows[r0][c4 * 4 + 3] = a3;
+        // the four row groups of a warp (lanes c4, c4+8, c4+16, c4+24) fold with two shuffle steps, fixed order
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, off); a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, off); a3 += __shfl_xor_sync(0xffffffffu, a3, off);
+        }
+        if ((threadIdx.x & 31) < 8) {
+            const unsigned w = threadIdx.x >> 5;
+            sRows[w][c4 * 4 + 0] = a0; sRows[w][c4 * 4 + 1] = a1; sRows[w][c4 * 4 + 2] = a2; sRows[w][c4 * 4 + 3] = a3;
+        }
     }
     __syncthreads();
     VH_TRACE(5);
     if (threadIdx.x < 32) {
-        const unsigned R = blockDim.x >> 3;
+        const unsigned nw = blockDim.x >> 5;
         double t = 0;
-        for (unsigned g = 0; g < R; ++g) t += sRows[g][threadIdx.x];
+        for (unsigned g = 0; g < nw; ++g) t += sRows[g][threadIdx.x];
         float f = (float)t;
         sSys[threadIdx.x] = f;
         if (threadIdx.x == 0) v.ctr->icpTicket = 0;

@@ -15,30 +15,60 @@ namespace vh {
 
 struct BlockCache { int x, y, z; const Voxel* vox; bool valid; };
 
-__device__ __forceinline__ bool voxelAt(const View& v, BlockCache& bc, int vx, int vy, int vz, float& sdf) {
+// is the block holding voxel (vx, vy, vz) allocated?  (one-entry cache: consecutive samples hit the same block)
+__device__ __forceinline__ bool blockAllocated(const View& v, BlockCache& bc, int vx, int vy, int vz) {
     const int bx = vx >> 3, by = vy >> 3, bz = vz >> 3;           // floor division by 8
     if (!(bc.valid && bc.x == bx && bc.y == by && bc.z == bz)) {
         int ptr = lookupBlock(v, bx, by, bz);
         bc.x = bx; bc.y = by; bc.z = bz; bc.valid = true;
         bc.vox = ptr >= 0 ? v.voxels + ptr : nullptr;
     }
-    if (bc.vox == nullptr) return false;
-    const float2 sw = __ldg(reinterpret_cast<const float2*>(bc.vox + (((vz & 7) * 64) + ((vy & 7) * 8) + (vx & 7))));
-    sdf = sw.x;
-    return sw.y > 0.0f;
+    return bc.vox != nullptr;
 }
 
-__device__ __forceinline__ bool sampleTrilinear(const View& v, BlockCache& bc, float px, float py, float pz, float& out) {
+// The 2x2x2 block neighbourhood anchored at the block of the sample's base voxel: a trilinear sample whose base
+// voxel sits on a block face needs 2, 4 or 8 blocks, and the samples of one ray stay in the same neighbourhood
+// for several steps.  r1 profile: with a one-entry cache the 8 taps of a face-straddling sample alternated
+// between two blocks and re-probed the hash table on every tap (dependent L2 round trips): 490 us per VGA frame.
+struct Hood { int bx, by, bz; int ptr[8]; unsigned have; bool valid; };
+
+__device__ __forceinline__ int hoodPtr(const View& v, Hood& h, int ci) {
+    if (!(h.have & (1u << ci))) {
+        h.ptr[ci] = lookupBlock(v, h.bx + (ci & 1), h.by + ((ci >> 1) & 1), h.bz + (ci >> 2));
+        h.have |= 1u << ci;
+    }
+    return h.ptr[ci];
+}
+
+__device__ __forceinline__ bool sampleTrilinear(const View& v, Hood& h, float px, float py, float pz, float& out) {
     const float gx = px * v.invVoxelSize, gy = py * v.invVoxelSize, gz = pz * v.invVoxelSize;
     const float fx0 = floorf(gx), fy0 = floorf(gy), fz0 = floorf(gz);
     const int x0 = f2i(fx0), y0 = f2i(fy0), z0 = f2i(fz0);
     const float ax = gx - fx0, ay = gy - fy0, az = gz - fz0;
-    float s[8];
+    const int bx = x0 >> 3, by = y0 >> 3, bz = z0 >> 3;           // floor division by 8
+    if (!(h.valid && h.bx == bx && h.by == by && h.bz == bz)) { h.bx = bx; h.by = by; h.bz = bz; h.have = 0; h.valid = true; }
+    const int lx = x0 & 7, ly = y0 & 7, lz = z0 & 7;
+    const int nx = lx == 7, ny = ly == 7, nz = lz == 7;           // does the +1 tap leave the anchor block?
+    // block pointers first (at most 8 probes, usually 1), then the eight voxel loads in flight together
+    const Voxel* vp[8];
+    bool ok = true;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (!voxelAt(v, bc, x0 + (k & 1), y0 + ((k >> 1) & 1), z0 + (k >> 2), s[k])) return false;
-    const float c00 = fmaf(ax, s[1] - s[0], s[0]), c10 = fmaf(ax, s[3] - s[2], s[2]);
-    const float c01 = fmaf(ax, s[5] - s[4], s[4]), c11 = fmaf(ax, s[7] - s[6], s[6]);
+    for (int k = 0; k < 8; ++k) {
+        const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+        const int ci = (dx & nx) | ((dy & ny) << 1) | ((dz & nz) << 2);
+        const int ptr = hoodPtr(v, h, ci);
+        ok = ok && ptr >= 0;
+        vp[k] = v.voxels + (ptr >= 0 ? ptr : 0) + ((((lz + dz) & 7) * 64) + (((ly + dy) & 7) * 8) + ((lx + dx) & 7));
+    }
+    if (!ok) return false;
+    float2 sw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sw[k] = __ldg(reinterpret_cast<const float2*>(vp[k]));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ok = ok && sw[k].y > 0.0f;
+    if (!ok) return false;
+    const float c00 = fmaf(ax, sw[1].x - sw[0].x, sw[0].x), c10 = fmaf(ax, sw[3].x - sw[2].x, sw[2].x);
+    const float c01 = fmaf(ax, sw[5].x - sw[4].x, sw[4].x), c11 = fmaf(ax, sw[7].x - sw[6].x, sw[6].x);
     const float c0 = fmaf(ay, c10 - c00, c00), c1 = fmaf(ay, c11 - c01, c01);
     out = fmaf(az, c1 - c0, c0);
     return true;
@@ -101,6 +131,9 @@ __global__ void __launch_bounds__(128) k_raycast(View v, const int* __restrict__
     const float dwz = sPose[8] * rd.x + sPose[9] * rd.y + sPose[10] * rd.z;
     const float ox = sPose[3], oy = sPose[7], oz = sPose[11];
     BlockCache bc{0, 0, 0, nullptr, false};
+    Hood hood;
+    hood.valid = false;
+    hood.have = 0;
     const int tile = (y / kTile) * ((v.W + kTile - 1) / kTile) + (x / kTile);
     const float tmin = __int_as_float(__ldg(tileMin + tile)), tmax = __int_as_float(__ldg(tileMax + tile));
     float z = fmaxf(v.depthMin, tmin - vs), zPrev = 0.f, sPrev = 0.f, zHit = 0.f;
@@ -109,7 +142,7 @@ __global__ void __launch_bounds__(128) k_raycast(View v, const int* __restrict__
     for (int it = 0; it < 4096 && z < zEnd; ++it) {
         const float px = fmaf(z, dwx, ox), py = fmaf(z, dwy, oy), pz = fmaf(z, dwz, oz);
         float s;
-        if (sampleTrilinear(v, bc, px, py, pz, s)) {
+        if (sampleTrilinear(v, hood, px, py, pz, s)) {
             if (havePrev && sPrev > 0.0f && s <= 0.0f) {
                 zHit = zPrev + (z - zPrev) * (sPrev / (sPrev - s));
                 hit = true;
@@ -119,11 +152,9 @@ __global__ void __launch_bounds__(128) k_raycast(View v, const int* __restrict__
             z += fmaxf(vs, 0.8f * s);
         } else {
             havePrev = false;
-            float dummy;
             const int vx = f2i(floorf(px * v.invVoxelSize + 0.5f)), vy = f2i(floorf(py * v.invVoxelSize + 0.5f)),
                       vz = f2i(floorf(pz * v.invVoxelSize + 0.5f));
-            voxelAt(v, bc, vx, vy, vz, dummy);
-            z += (bc.vox != nullptr) ? vs : coarse;
+            z += blockAllocated(v, bc, vx, vy, vz) ? vs : coarse;
         }
     }
     float4 vo = make_float4(0.f, 0.f, 0.f, 1.0f), no = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -131,9 +162,9 @@ __global__ void __launch_bounds__(128) k_raycast(View v, const int* __restrict__
         const float hx = fmaf(zHit, dwx, ox), hy = fmaf(zHit, dwy, oy), hz = fmaf(zHit, dwz, oz);
         vo = make_float4(rd.x * zHit, rd.y * zHit, rd.z * zHit, 1.0f);
         float gxp, gxm, gyp, gym, gzp, gzm;
-        const bool ok = sampleTrilinear(v, bc, hx + vs, hy, hz, gxp) && sampleTrilinear(v, bc, hx - vs, hy, hz, gxm) &&
-                        sampleTrilinear(v, bc, hx, hy + vs, hz, gyp) && sampleTrilinear(v, bc, hx, hy - vs, hz, gym) &&
-                        sampleTrilinear(v, bc, hx, hy, hz + vs, gzp) && sampleTrilinear(v, bc, hx, hy, hz - vs, gzm);
+        const bool ok = sampleTrilinear(v, hood, hx + vs, hy, hz, gxp) && sampleTrilinear(v, hood, hx - vs, hy, hz, gxm) &&
+                        sampleTrilinear(v, hood, hx, hy + vs, hz, gyp) && sampleTrilinear(v, hood, hx, hy - vs, hz, gym) &&
+                        sampleTrilinear(v, hood, hx, hy, hz + vs, gzp) && sampleTrilinear(v, hood, hx, hy, hz - vs, gzm);
         if (ok) {
             const float gx = gxp - gxm, gy = gyp - gym, gz = gzp - gzm;
             const float cxn = sPose[0] * gx + sPose[4] * gy + sPose[8] * gz;     // R^T g: world -> camera

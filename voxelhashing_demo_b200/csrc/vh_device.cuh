@@ -124,13 +124,11 @@ __device__ __forceinline__ bool sameKey(int4 e, int x, int y, int z) { return e.
 __device__ __forceinline__ int lookupBlock(const View& v, int x, int y, int z) {
     unsigned h = bucketOf(v, x, y, z);
     unsigned base = h * v.bucketSize;
-    for (unsigned i0 = 0; i0 < v.bucketSize; i0 += 8) {        // up to 8 slots' loads in flight together
-        int4 e[8];
-#pragma unroll
-        for (unsigned k = 0; k < 8; ++k) e[k] = (i0 + k < v.bucketSize) ? __ldg(v.entries + base + i0 + k) : freeSlot();
-#pragma unroll
-        for (unsigned k = 0; k < 8; ++k)
-            if (sameKey(e[k], x, y, z) && e[k].w != VH_FREE_BLOCK) return e[k].w;
+    for (unsigned i = 0; i < v.bucketSize; ++i) {               // most hits are in slot 0 or 1: probe in order
+        int4 e = __ldg(v.entries + base + i);
+        if (sameKey(e, x, y, z) && e.w != VH_FREE_BLOCK) return e.w;
+        if (e.w == VH_FREE_BLOCK && e.x == VH_FREE_COORD) return VH_FREE_BLOCK;   // never-used slot: slots fill in order, so
+                                                                                  // nothing lives behind it (nor in the chain)
     }
     unsigned cur = base + v.bucketSize - 1;
     for (unsigned n = 0; n < v.chainMax; ++n) {
