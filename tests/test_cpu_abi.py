@@ -100,3 +100,24 @@ def test_sass_has_the_blackwell_paths(built_library):
     assert "ATOMG.E.CAS.128" in sass
     assert "LDG.E.128" in sass and "STG.E.128" in sass
     assert "MATCH.ANY" in sass and "REDUX" in sass or "MATCH.ANY" in sass
+
+
+def test_invalid_configs_are_rejected_before_touching_a_device(built_library):
+    lib = L.load_library()
+    for kw in (dict(numBuckets=0), dict(numVoxelBlocks=0), dict(voxelSize=0.0), dict(width=0), dict(numVoxelBlocks=5_000_000)):
+        h = C.c_void_p()
+        c = Config(**kw).to_c()
+        assert lib.vh_create(C.byref(c), C.byref(h)) == L.VH_ERR_INVALID and not h, kw
+        assert lib.vh_last_error()
+    c = Config().to_c()
+    c.table.voxelBlockSize = 4
+    h = C.c_void_p()
+    assert lib.vh_create(C.byref(c), C.byref(h)) == L.VH_ERR_INVALID
+    assert lib.vh_create(None, C.byref(h)) == L.VH_ERR_INVALID
+    # every handle call refuses a null context instead of crashing
+    null = C.c_void_p()
+    assert lib.vh_compact(null, None) == L.VH_ERR_INVALID
+    assert lib.vh_alloc_blocks(null, None, None, None) == L.VH_ERR_INVALID
+    assert lib.vh_icp_align(null, None, None, None, None, 1, None) == L.VH_ERR_INVALID
+    assert lib.vh_raycast(null, None, None, None) == L.VH_ERR_INVALID
+    assert lib.vh_set_peers(null, 0, 1, None) == L.VH_ERR_INVALID

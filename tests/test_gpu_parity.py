@@ -585,3 +585,97 @@ def test_full_size_properties(built_library, oracle, name):
     rep, nvis, nupd = ot.fuse_frame(pose, ov, odf)
     assert (rep.inserted, nvis, nupd) == (s1.numAllocated, s1.numVisible, int(s1.numUpdated))
     assert entries_to_set(ent) == entries_to_set(ot.entries())
+
+
+# ---- edge cases: empty, ragged, degenerate inputs -----------------------------------------------------
+@pytest.mark.parametrize("policy", [POLICY_REF_EXACT, POLICY_FIXED])
+def test_empty_frame_is_a_no_op(built_library, oracle, policy):
+    """An all-zero depth image: nothing requested, nothing visible, nothing integrated, ICP declines to solve."""
+    cfg = fixed_cfg(numVoxelBlocks=512) if policy == POLICY_FIXED else Config(numVoxelBlocks=512)
+    depth = np.zeros((cfg.height, cfg.width), np.uint16)
+    ctx = Context(cfg)
+    v, n, df = gpu_preprocess(ctx, depth)
+    assert not v[:, :3].any().item() and not n.any().item()
+    ctx.fuse_frame(np.eye(4, dtype=np.float32), v, n, df if policy == POLICY_FIXED else None)
+    st = ctx.stats()
+    assert (st.numAllocated, st.numVisible, int(st.numUpdated), st.dropped) == (0, 0, 0, 0)
+    assert len(ctx.export_entries()) == 0
+    ctx.icp_reset(True)
+    ctx.icp_align(v, n, v, n, 3)
+    delta, twist, sysv = ctx.icp_get()
+    assert np.array_equal(delta, np.eye(4, dtype=np.float32)) and not twist.any() and sysv[28] == 0
+    if policy == POLICY_FIXED:
+        rv, rn = torch.ones_like(v), torch.ones_like(n)
+        ctx.raycast(rv, rn)
+        torch.cuda.synchronize()
+        assert not rv[:, :3].any().item() and not rn.any().item()
+
+
+@pytest.mark.parametrize("policy", [POLICY_REF_EXACT, POLICY_FIXED])
+def test_ragged_image_size_all_stages(built_library, oracle, policy):
+    """161 x 123: not a multiple of any tile (32x8 alloc / preprocess tiles, 16x8 raycast tiles, 5-pixel ICP batches)."""
+    kw = dict(width=161, height=123, fx=517.3 / 4, fy=516.5 / 4, cx=318.6 / 4, cy=255.3 / 4, numVoxelBlocks=4096)
+    cfg = fixed_cfg(icpNormalThres=0.8, **kw) if policy == POLICY_FIXED else Config(**kw)
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    maps = []
+    for k in (0, 9):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        depth = render(cfg, scenes.scene_S1T(), pose)
+        ov, on, odf = ot.preprocess(depth)
+        v, n, df = gpu_preprocess(ctx, depth)
+        assert np.array_equal(bits(v.cpu().numpy()), bits(ov)) and np.array_equal(bits(n.cpu().numpy()), bits(on))
+        if policy == POLICY_FIXED:
+            ot.fuse_frame(pose, ov, odf)
+            ctx.fuse_frame(pose, v, n, df)
+        else:
+            ref_fuse_cpu(ot, pose, ov)
+            ref_fuse_gpu(ctx, pose, v, n)
+        maps.append((ov, on, v, n))
+    exact, _ = compare_blocks(ctx.block_dict(), ot.block_dict())
+    assert exact
+    (tv, tn, gtv, gtn), (iv, inn, giv, gin) = maps
+    ctx.icp_reset(True)
+    ctx.icp_align(giv, gin, gtv, gtn, 10)
+    g = ctx.icp_get()[0]
+    _, _, o = oracle.icp_align(cfg, iv, inn, tv, tn, 10)
+    assert rot_err(g[:3, :3], o[:3, :3]) <= 1e-4 and np.max(np.abs(g[:3, 3] - o[:3, 3])) <= 1e-4
+
+
+def test_table_and_chain_full_drops_are_counted(built_library, oracle):
+    """4 buckets x 1 slot + chains of 2: at most 12 blocks fit; the rest are dropped, counted, never duplicated."""
+    cfg = fixed_cfg(numBuckets=4, bucketSize=1, attachedLinkedListSize=2, overflowSlots=64, numVoxelBlocks=1024,
+                    width=160, height=120, fx=517.3 / 4, fy=516.5 / 4, cx=318.6 / 4, cy=255.3 / 4)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    ctx = Context(cfg)
+    v, n, df = gpu_preprocess(ctx, depth)
+    for _ in range(2):
+        ctx.fuse_frame(np.eye(4, dtype=np.float32), v, n, df)
+    st = ctx.stats()
+    ent = ctx.export_entries()
+    live = ent[ent["ptr"] >= 0]
+    assert st.dropped > 0 and 0 < len(live) <= 4 * (1 + 2) and st.numAllocated == len(live)
+    assert len(entries_to_set(live)) == len(live)
+    ot = oracle.OracleTable(cfg)
+    ov, _, odf = ot.preprocess(depth)
+    ot.fuse_frame(np.eye(4), ov, odf)
+    assert len(ot.entries()) == len(live)          # capacity is order-independent even if the survivors are not
+
+
+def test_large_rotation_and_far_translation_pose(built_library, oracle):
+    """Negative block coordinates, a 90-degree yaw and a far offset: hash, floor division and frustum math."""
+    cfg = fixed_cfg(numVoxelBlocks=8192)
+    pose = (scenes.trans(-7.3, 2.1, -4.9) @ scenes.rot_y(90.0)).astype(np.float32)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))       # the camera sees S1 from its own frame
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    ov, _, odf = ot.preprocess(depth)
+    rep, nvis, nupd = ot.fuse_frame(pose, ov, odf)
+    v, n, df = gpu_preprocess(ctx, depth)
+    ctx.fuse_frame(pose, v, n, df)
+    st = ctx.stats()
+    keys = entries_to_set(ctx.export_entries())
+    assert keys == entries_to_set(ot.entries()) and min(k[0] for k in keys) < -40 and min(k[2] for k in keys) < -20
+    assert (st.numVisible, int(st.numUpdated)) == (nvis, nupd)
+    exact, _ = compare_blocks(ctx.block_dict(), ot.block_dict())
+    assert exact
