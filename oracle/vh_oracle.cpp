@@ -598,22 +598,31 @@ static long long integrateImpl(vo_table* t, const float* pose, const float* dept
         // Niessner's weight max(ws * 1.5 * (1 - (d - dmin)/(dmax - dmin)), 1) as one FMA in d (ref VoxelUtils.cu:809-827)
         const float wA = -((ws * 1.5f) * invRange);
         const float wB = (ws * 1.5f) * (1.0f + c.depthMin * invRange);
+        // K, the inverse pose and the voxel size as one 3x4 matrix, voxel index -> (u z, v z, z)
+        float M[12];
+        for (int col = 0; col < 4; ++col) {
+            const float sc = col < 3 ? c.voxelSize : 1.0f;
+            M[0 + col] = fmaf(fx, inv[0 + col], cx * inv[8 + col]) * sc;
+            M[4 + col] = fmaf(fy, inv[4 + col], cy * inv[8 + col]) * sc;
+            M[8 + col] = inv[8 + col] * sc;
+        }
+        const float zFar = fmaf(c.truncScale, c.depthMax, c.truncation) + c.depthMax;
 #pragma omp parallel for schedule(dynamic, 8) reduction(+ : updated)
         for (int bi = 0; bi < n; ++bi) {
             const Entry& e = t->compact[bi];
             for (int tz = 0; tz < 8; ++tz)
                 for (int ty = 0; ty < 8; ++ty)
                     for (int tx = 0; tx < 8; ++tx) {
-                        float X = (float)(e.pos.x * 8 + tx) * c.voxelSize;
-                        float Y = (float)(e.pos.y * 8 + ty) * c.voxelSize;
-                        float Z = (float)(e.pos.z * 8 + tz) * c.voxelSize;
-                        float pcx = fmaf(inv[0], X, fmaf(inv[1], Y, fmaf(inv[2], Z, inv[3])));
-                        float pcy = fmaf(inv[4], X, fmaf(inv[5], Y, fmaf(inv[6], Z, inv[7])));
-                        float pcz = fmaf(inv[8], X, fmaf(inv[9], Y, fmaf(inv[10], Z, inv[11])));
-                        if (!(pcz > 0.0f)) continue;
+                        // the kernel's thread owns voxels (tx & 4) .. (tx & 4) + 3 and steps in float
+                        float X = (float)(int)((uint32_t)e.pos.x * 8u + (uint32_t)(tx & 4)) + (float)(tx & 3);
+                        float Y = (float)(int)((uint32_t)e.pos.y * 8u + (uint32_t)ty);
+                        float Z = (float)(int)((uint32_t)e.pos.z * 8u + (uint32_t)tz);
+                        float pa = fmaf(M[0], X, fmaf(M[1], Y, fmaf(M[2], Z, M[3])));     // u * z
+                        float pb = fmaf(M[4], X, fmaf(M[5], Y, fmaf(M[6], Z, M[7])));     // v * z
+                        float pcz = fmaf(M[8], X, fmaf(M[9], Y, fmaf(M[10], Z, M[11])));  // z
+                        if (!(pcz > 1e-6f && pcz < zFar)) continue;
                         float iz = 1.0f / pcz;
-                        float u = fmaf(pcx * iz, fx, cx), v = fmaf(pcy * iz, fy, cy);
-                        int px = roundPixel(u), py = roundPixel(v);            // nearest pixel, ties to even
+                        int px = roundPixel(pa * iz), py = roundPixel(pb * iz);        // nearest pixel, ties to even
                         if ((unsigned)px >= (unsigned)W || (unsigned)py >= (unsigned)H) continue;
                         float d = depthSrc[(size_t)(py * W + px) * stride + zoff];
                         if (!(d > c.depthMin && d < c.depthMax)) continue;

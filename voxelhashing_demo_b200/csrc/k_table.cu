@@ -70,6 +70,14 @@ __global__ void k_set_frame(View v, FrameParams* frame, Pose16 hostPose, const f
     float inv[16];
     inverse4(p, inv);
     for (int i = 0; i < 16; ++i) { frame->pose[i] = p[i]; frame->inv[i] = inv[i]; }
+    // Fixed integration matrix: voxel index (i,j,k,1) -> (u*z, v*z, z) in one 3x4 product
+    for (int c = 0; c < 4; ++c) {
+        const float sc = c < 3 ? v.voxelSize : 1.0f;
+        frame->proj[0 + c] = fmaf(v.fx, inv[0 + c], v.cx * inv[8 + c]) * sc;
+        frame->proj[4 + c] = fmaf(v.fy, inv[4 + c], v.cy * inv[8 + c]) * sc;
+        frame->proj[8 + c] = inv[8 + c] * sc;
+        frame->proj[12 + c] = 0.0f;
+    }
     if (d_poseOut) for (int i = 0; i < 16; ++i) d_poseOut[i] = p[i];
     v.ctr->compactCount = 0;     // ref flattenIntoBuffer: cudaMemset(counter, 0), VoxelUtils.cu:760
     v.ctr->numUpdated = 0ull;

@@ -61,6 +61,7 @@ void fillView(vh_context* c) {
     // Niessner's weight max(wSample * 1.5 * (1 - (d - dmin)/(dmax - dmin)), 1) as one FMA in d (ref VoxelUtils.cu:809-827)
     v.wA = -((v.wSample * 1.5f) * v.invDepthRange);
     v.wB = (v.wSample * 1.5f) * (1.0f + g.depthMin * v.invDepthRange);
+    v.zFar = fmaf(v.truncScale, v.depthMax, v.truncation) + v.depthMax;
     v.W = g.width;
     v.H = g.height;
     v.fx = g.fx; v.fy = g.fy; v.cx = g.cx; v.cy = g.cy;

@@ -40,6 +40,7 @@ struct Counters {
 struct FrameParams {
     float pose[16];   // camera -> world, row-major (HashTableParams::global_transform)
     float inv[16];    // world -> camera (inv_global_transform), adjugate inverse as SDF_Hashtable.cpp:15
+    float proj[16];   // Fixed integration: rows 0-2 = K * inv[0:3,:] * diag(voxelSize,voxelSize,voxelSize,1), voxel INDEX -> (u*z, v*z, z)
 };
 
 struct IcpState {
@@ -66,6 +67,7 @@ struct View {
     float voxelSize, invVoxelSize, truncation, truncScale, wMax, wSample;
     float depthMin, depthMax, invDepthRange, depthScale;
     float wA, wB;                        // Fixed sample weight: w = max(wA * depth + wB, 1)
+    float zFar;                          // Fixed integration: no voxel deeper than depthMax + truncation(depthMax) can be updated
     int W, H;
     float fx, fy, cx, cy;
     float K[9], Kinv[9];                 // tracking-side intrinsics (SetCameraIntrinsic)
