@@ -51,10 +51,11 @@ inline int f2i_rn(float x) {
     if (x <= -2147483648.0f) return kIntMin;
     return (int)std::nearbyintf(x);
 }
-// pixel rounding of the Fixed integration: nearest, ties to even, via the 1.5*2^23 trick;
-// bit-identical to nearbyintf for |u| < 2^22, far outside any image beyond that
-inline int roundPixel(float u) {
-    float t = u + 12582912.0f;
+// pixel rounding of the Fixed integration: nearest, ties to even, via the 1.5*2^23 trick
+// (bit-identical to nearbyintf for |u| < 2^22, far outside any image beyond that);
+// the integration's own form: nearest integer of a * r with ONE rounding (the product is never rounded to float)
+inline int roundPixelFma(float a, float r) {
+    float t = fmaf(a, r, 12582912.0f);
     int32_t bits;
     std::memcpy(&bits, &t, sizeof(bits));
     return (int)(bits - 0x4B400000);
@@ -622,7 +623,8 @@ static long long integrateImpl(vo_table* t, const float* pose, const float* dept
                         float pcz = fmaf(M[8], X, fmaf(M[9], Y, fmaf(M[10], Z, M[11])));  // z
                         if (!(pcz > 1e-6f && pcz < zFar)) continue;
                         float iz = 1.0f / pcz;
-                        int px = roundPixel(pa * iz), py = roundPixel(pb * iz);        // nearest pixel, ties to even
+                        // nearest pixel, ties to even: product and 1.5*2^23 bias in one fma (a single rounding)
+                        int px = roundPixelFma(pa, iz), py = roundPixelFma(pb, iz);
                         if ((unsigned)px >= (unsigned)W || (unsigned)py >= (unsigned)H) continue;
                         float d = depthSrc[(size_t)(py * W + px) * stride + zoff];
                         if (!(d > c.depthMin && d < c.depthMax)) continue;
