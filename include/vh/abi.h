@@ -104,7 +104,8 @@ enum vh_status {
     VH_ERR_INVALID = 1,     /* bad argument */
     VH_ERR_CUDA = 2,        /* CUDA runtime error; see vh_last_error() */
     VH_ERR_NO_DEVICE = 3,   /* no CUDA device: there is no CPU fallback */
-    VH_ERR_CAPACITY = 4     /* table / heap / overflow arena exhausted */
+    VH_ERR_CAPACITY = 4,    /* table / heap / overflow arena exhausted */
+    VH_ERR_UNSUPPORTED = 5  /* operation not defined for this context's policy */
 };
 
 /* Arithmetic policy: same kernels, same memory traffic. */
@@ -137,6 +138,7 @@ typedef struct vh_stats {
     int dropped;            /* requests dropped since creation (bucket/chain/heap full) */
     unsigned long long numUpdated;   /* voxels updated by the last integrate call */
     int lastInserted;       /* blocks inserted by the last allocation call */
+    int lastFreed;          /* blocks released by the last vh_garbage_collect call */
 } vh_stats;
 
 /* ICP normal equations, (v, omega) unknown order (ref Solver.cu:25-37, SE3.cpp:4-19):
@@ -185,6 +187,18 @@ int vh_fuse_frame(vh_context* ctx, const float4* d_verts, const float4* d_normal
                   const float* d_depthf_or_null, vh_stream s);
 /* Synchronises the stream and copies the counters back. */
 int vh_get_stats(vh_context* ctx, vh_stats* out, vh_stream s);
+/* Voxel starvation + block garbage collection (Fixed policy only).  The reference's removal
+ * path is dead and wrong (deleteVoxelEntry, VoxelUtils.cu:544-604; removeSingleBlockInHeap :336-341 is followed for
+ * the heap push); the pass is the one of the paper the reference implements (Niessner et al. 2013, section 4.4).
+ * For every block in scope -- VH_GC_VISIBLE: the list of the last vh_compact; VH_GC_ALL: every allocated block --
+ *   weight <- max(weight - weight_decay, 0) for every voxel          (skipped when weight_decay <= 0)
+ *   release the block when no voxel has weight > 0, or min |sdf| over the voxels with weight > 0 >= sdf_threshold
+ *   (sdf_threshold <= 0 selects truncation + truncScale * depthMax).
+ * A released block's voxels are zeroed, its hash slot becomes a tombstone that later allocations reclaim, and its id
+ * goes back on the heap.  The visible list is emptied: call vh_compact before the next vh_integrate / vh_raycast. */
+#define VH_GC_VISIBLE 0
+#define VH_GC_ALL 1
+int vh_garbage_collect(vh_context* ctx, int scope, float sdf_threshold, float weight_decay, vh_stream s);
 
 /* ---- tracking (ref CameraTracking.cpp:26-69, Solver.cpp:48-124) ------------------------ */
 /* One fused Gauss-Newton iteration on the device: association + residual + 27-sum reduction

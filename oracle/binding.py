@@ -74,6 +74,8 @@ def oracle_lib() -> C.CDLL:
     lib.vo_last_requested_new.restype = I
     lib.vo_compact.argtypes = [P, P]
     lib.vo_compact.restype = I
+    lib.vo_garbage_collect.argtypes = [P, I, C.c_float, C.c_float]
+    lib.vo_garbage_collect.restype = I
     lib.vo_integrate.argtypes = [P, P, P]
     lib.vo_integrate.restype = C.c_longlong
     lib.vo_integrate_depthf.argtypes = [P, P, P]
@@ -200,6 +202,9 @@ class OracleTable:
     def integrate_depthf(self, pose, depthf) -> int:
         p, v = f32(pose).reshape(16), f32(depthf)
         return int(self.lib.vo_integrate_depthf(self.h, p.ctypes.data, v.ctypes.data))
+
+    def garbage_collect(self, scope=0, sdf_threshold=0.0, weight_decay=0.0) -> int:
+        return int(self.lib.vo_garbage_collect(self.h, int(scope), float(sdf_threshold), float(weight_decay)))
 
     def fuse_frame(self, pose, verts, depthf=None):
         rep = self.alloc(pose, verts)

@@ -273,34 +273,52 @@ int insertRef(vo_table* t, I3 key) {
 }
 
 // Fixed: bucket slots, then the overflow chain hanging off the bucket's last slot.
+// Slot states as in k_alloc.cu: never used {INT_MAX^3, -1}, live, tombstone {old key, -1} (left by garbage
+// collection).  The key goes into the FIRST claimable slot of the scan order, after the scan has shown it is not
+// stored further on; a never-used slot ends the scan (slots fill in scan order).
 // Returns 1 inserted, 0 present, -1 dropped.
 int insertFixed(vo_table* t, I3 key) {
     const vo_config& c = t->cfg;
     const unsigned S = c.numBuckets * c.bucketSize;
     unsigned h = hashBlock(c, key);
     unsigned start = h * c.bucketSize;
-    for (unsigned i = 0; i < c.bucketSize; ++i) {
-        Entry& e = t->table[start + i];
+    int claim = -1;
+    bool ended = false;
+    for (unsigned i = 0; i < c.bucketSize && !ended; ++i) {
+        const Entry& e = t->table[start + i];
         if (e.ptr != kFree) { if (e.pos == key) return 0; continue; }
+        if (claim < 0) claim = (int)(start + i);
+        ended = e.pos.x == kIntMax;
+    }
+    unsigned cur = start + c.bucketSize - 1;
+    unsigned len = 0;
+    if (!ended) {
+        while (t->table[cur].offset != 0) {
+            cur = cur + (unsigned)t->table[cur].offset;
+            ++len;
+            const Entry& e = t->table[cur];
+            if (e.ptr != kFree) { if (e.pos == key) return 0; }
+            else if (claim < 0) claim = (int)cur;
+        }
+    }
+    if (claim >= 0) {
+        Entry& e = t->table[claim];
         int id = popHeap(t);
-        if (id < 0) { t->heapCounter++; t->dropped++; return -1; }
+        if (id < 0) {                                   // heap empty: never-used bucket slot stays free, anything else a tombstone
+            t->heapCounter++; t->dropped++;
+            if (e.pos.x != kIntMax || (unsigned)claim >= S) e.pos = key;
+            return -1;
+        }
         e.pos = key; e.ptr = id * 512;
         return 1;
     }
-    // chain
-    unsigned cur = start + c.bucketSize - 1;
-    unsigned len = 0;
-    while (t->table[cur].offset != 0) {
-        cur = cur + (unsigned)t->table[cur].offset;
-        ++len;
-        if (t->table[cur].pos == key && t->table[cur].ptr != kFree) return 0;
-    }
     if (len >= c.attachedLinkedListSize || (unsigned)t->overflowUsed >= c.overflowSlots) { t->dropped++; return -1; }
-    int id = popHeap(t);
-    if (id < 0) { t->heapCounter++; t->dropped++; return -1; }
     unsigned slot = S + (unsigned)t->overflowUsed++;
-    t->table[slot].pos = key; t->table[slot].ptr = id * 512; t->table[slot].offset = 0;
+    t->table[slot].pos = key; t->table[slot].ptr = kFree; t->table[slot].offset = 0;
     t->table[cur].offset = (int)(slot - cur);
+    int id = popHeap(t);
+    if (id < 0) { t->heapCounter++; t->dropped++; return -1; }     // linked tombstone, as on the device
+    t->table[slot].ptr = id * 512;
     return 1;
 }
 
@@ -648,6 +666,41 @@ static long long integrateImpl(vo_table* t, const float* pose, const float* dept
 
 long long vo_integrate(vo_table* t, const float* pose, const float* verts) { return integrateImpl(t, pose, verts, 4, 2); }
 long long vo_integrate_depthf(vo_table* t, const float* pose, const float* depthf) { return integrateImpl(t, pose, depthf, 1, 0); }
+
+// ---- starvation + garbage collection (k_gc.cu; Niessner et al. 2013, section 4.4) ---------------------
+// scope 0: blocks of the last vo_compact; scope 1: every allocated block.  Returns the number released.
+int vo_garbage_collect(vo_table* t, int scope, float sdfThreshold, float weightDecay) {
+    const vo_config& c = t->cfg;
+    if (!(sdfThreshold > 0.0f)) sdfThreshold = fmaf(c.truncScale, c.depthMax, c.truncation);
+    std::vector<size_t> slots;
+    if (scope == 0) {
+        for (const Entry& ce : t->compact) {
+            const Entry* e = findEntry(t, ce.pos);
+            if (e && e->ptr == ce.ptr) slots.push_back((size_t)(e - t->table.data()));
+        }
+    } else {
+        for (size_t i = 0; i < t->table.size(); ++i) if (t->table[i].ptr != kFree) slots.push_back(i);
+    }
+    int freed = 0;
+    for (size_t si : slots) {
+        Entry& e = t->table[si];
+        float* vox = t->voxels + (size_t)e.ptr * 2;
+        float mn = INFINITY, mx = 0.0f;
+        for (int k = 0; k < 512; ++k) {
+            float w = vox[2 * k + 1];
+            if (weightDecay > 0.0f) { w = fmaxf(w - weightDecay, 0.0f); vox[2 * k + 1] = w; }
+            if (w > 0.0f) { mn = fminf(mn, fabsf(vox[2 * k])); mx = fmaxf(mx, w); }
+        }
+        if (mx == 0.0f || mn >= sdfThreshold) {
+            std::memset(vox, 0, sizeof(float) * 1024);
+            t->heap[++t->heapCounter] = (unsigned)(e.ptr / 512);      // ref removeSingleBlockInHeap :338-339
+            e.ptr = kFree;                                           // tombstone: pos and chain link stay
+            ++freed;
+        }
+    }
+    t->compact.clear();
+    return freed;
+}
 
 // ---- export ---------------------------------------------------------------------------------------
 int vo_num_allocated(vo_table* t) {

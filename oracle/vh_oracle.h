@@ -84,6 +84,9 @@ long long vo_integrate(vo_table* t, const float* pose, const float* verts);
 /* Fixed fast path: dense metric depth. */
 long long vo_integrate_depthf(vo_table* t, const float* pose, const float* depthf);
 
+/* Starvation + garbage collection (mirror of vh_garbage_collect).  scope 0 = last compaction, 1 = all.  Returns #released. */
+int  vo_garbage_collect(vo_table* t, int scope, float sdfThreshold, float weightDecay);
+
 /* Table export. entries: 5 ints each (x,y,z,ptr,offset), allocated entries only. */
 int  vo_num_allocated(vo_table* t);
 int  vo_export_entries(vo_table* t, int* entries5, int cap);

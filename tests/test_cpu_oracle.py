@@ -345,3 +345,38 @@ def test_golden_reference_icp(oracle):
     its, est, delta = oracle.icp_align(cfg, iv, None, tv, tn, 20)
     assert its == int(g["align_iters"])
     assert rot_err(delta[:3, :3], g["align_delta"][:3, :3]) <= 1e-4 and np.max(np.abs(delta[:3, 3] - g["align_delta"][:3, 3])) <= 1e-4
+
+
+def test_garbage_collection_semantics(oracle):
+    """Niessner 4.4 on the oracle: unobserved blocks go, starved blocks go, tombstones are reclaimed, nothing duplicates."""
+    cfg = small_cfg(policy=POLICY_FIXED, numBuckets=64, bucketSize=2, attachedLinkedListSize=8, overflowSlots=4096,
+                    numVoxelBlocks=4096, truncation=0.06)
+    pose = np.eye(4, dtype=np.float32)
+    depth = render(cfg, scenes.scene_S1(), pose)
+    ot = oracle.OracleTable(cfg)
+    v, _, df = ot.preprocess(depth)
+    ot.fuse_frame(pose, v, df)
+    before = ot.block_dict()
+    unobserved = {k for k, b in before.items() if not (b[:, 1] > 0).any()}
+    n0, h0 = len(before), ot.heap_counter()
+    freed = ot.garbage_collect(scope=1)
+    after = ot.block_dict()
+    assert freed == len(unobserved) and set(before) - set(after) == unobserved and ot.heap_counter() == h0 + freed
+    assert all(np.array_equal(after[k], before[k]) for k in after)
+    # same frame again: the released keys come back through reclaimed tombstones, values as after two fusions of a fresh table
+    ot.fuse_frame(pose, v, df)
+    again = ot.block_dict()
+    assert set(again) == set(before) and len(entries_to_set(ot.entries())) == len(ot.entries()) == n0
+    fresh = oracle.OracleTable(cfg)
+    fresh.fuse_frame(pose, v, df)
+    fresh.fuse_frame(pose, v, df)
+    f2 = fresh.block_dict()
+    assert all(np.array_equal(again[k], f2[k]) for k in again)
+    # starve everything: weights drop to 0, every block is released, the heap is whole again, the voxels are zero
+    assert ot.garbage_collect(scope=1, weight_decay=1e9) == n0
+    assert len(ot.entries()) == 0 and ot.heap_counter() == cfg.numVoxelBlocks - 1
+    ot.fuse_frame(pose, v, df)
+    once = oracle.OracleTable(cfg)
+    once.fuse_frame(pose, v, df)
+    a, b = ot.block_dict(), once.block_dict()
+    assert set(a) == set(b) and all(np.array_equal(a[k], b[k]) for k in a)

@@ -679,3 +679,95 @@ def test_large_rotation_and_far_translation_pose(built_library, oracle):
     assert (st.numVisible, int(st.numUpdated)) == (nvis, nupd)
     exact, _ = compare_blocks(ctx.block_dict(), ot.block_dict())
     assert exact
+
+
+# ---- starvation + garbage collection ----------------------------------------------------
+def _same_model(ctx, ot):
+    st = ctx.stats()
+    ent = ctx.export_entries()
+    assert entries_to_set(ent) == entries_to_set(ot.entries()) and len(entries_to_set(ent)) == len(ent)
+    assert st.heapCounter == ot.heap_counter()
+    exact, _ = compare_blocks(ctx.block_dict(), ot.block_dict())
+    assert exact
+
+
+@pytest.mark.parametrize("chained", [False, True])
+def test_garbage_collect_matches_oracle(built_library, oracle, chained):
+    """Release, tombstone reuse and starvation against the oracle; chained=True forces most blocks into overflow chains."""
+    kw = dict(numBuckets=64, bucketSize=2, attachedLinkedListSize=64) if chained else {}
+    cfg = fixed_cfg(numVoxelBlocks=4096, width=160, height=120, fx=517.3 / 4, fy=516.5 / 4, cx=318.6 / 4, cy=255.3 / 4, **kw)
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    frames = []
+    for k in (0, 12):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        depth = render(cfg, scenes.scene_S1(), pose)
+        ov, _, odf = ot.preprocess(depth)
+        v, n, df = gpu_preprocess(ctx, depth)
+        frames.append((pose, ov, odf, v, n, df))
+        ot.fuse_frame(pose, ov, odf)
+        ctx.fuse_frame(pose, v, n, df)
+    _same_model(ctx, ot)
+    # 1. default criterion over every block: only never-observed blocks go
+    freed = ot.garbage_collect(scope=1)
+    ctx.garbage_collect(L.VH_GC_ALL)
+    st = ctx.stats()
+    assert freed > 0 and st.lastFreed == freed and st.numVisible == 0
+    _same_model(ctx, ot)
+    # 2. fuse again: the released keys are re-requested and land in reclaimed tombstones
+    pose, ov, odf, v, n, df = frames[0]
+    ot.fuse_frame(pose, ov, odf)
+    ctx.fuse_frame(pose, v, n, df)
+    _same_model(ctx, ot)
+    # 3. visible scope with ageing and a tight |sdf| threshold: only blocks of the current view are touched
+    pose, ov, odf, v, n, df = frames[1]
+    nvis = ot.compact(pose)
+    ctx.set_pose(pose)
+    ctx.compact()
+    assert ctx.stats().numVisible == nvis
+    freed = ot.garbage_collect(scope=0, sdf_threshold=0.03, weight_decay=2.5)
+    ctx.garbage_collect(L.VH_GC_VISIBLE, 0.03, 2.5)
+    assert freed > 0 and ctx.stats().lastFreed == freed
+    _same_model(ctx, ot)
+    # 4. starve everything, then rebuild: identical to a model that never saw the first frames
+    n_all = len(ot.entries())
+    assert ot.garbage_collect(scope=1, weight_decay=1e9) == n_all
+    ctx.garbage_collect(L.VH_GC_ALL, 0.0, 1e9)
+    st = ctx.stats()
+    assert st.lastFreed == n_all and st.numAllocated == 0 and len(ctx.export_entries()) == 0
+    pose, ov, odf, v, n, df = frames[0]
+    ot.fuse_frame(pose, ov, odf)
+    ctx.fuse_frame(pose, v, n, df)
+    _same_model(ctx, ot)
+    fresh = Context(cfg)
+    fresh.fuse_frame(pose, v, n, df)
+    exact, _ = compare_blocks(ctx.block_dict(), fresh.block_dict())
+    assert exact, "released blocks were not zeroed"
+    # the raycaster walks through tombstones: same image as from the fresh model
+    if not chained:
+        ra, rb = ctx.new_maps()[:2], fresh.new_maps()[:2]
+        for c, r in ((ctx, ra), (fresh, rb)):
+            c.set_pose(pose)
+            c.raycast(*r)
+        torch.cuda.synchronize()
+        assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
+
+
+def test_garbage_collect_checkpoint_and_policy(built_library, oracle, tmp_path):
+    cfg = fixed_cfg(numVoxelBlocks=2048)
+    depth = render(cfg, scenes.scene_S1(), np.eye(4))
+    a = Context(cfg)
+    v, n, df = gpu_preprocess(a, depth)
+    pose = np.eye(4, dtype=np.float32)
+    a.fuse_frame(pose, v, n, df)
+    a.garbage_collect(L.VH_GC_ALL)                          # leaves holes in the id range
+    assert a.stats().lastFreed > 0
+    a.save(tmp_path / "gc.vhb")
+    b = Context(cfg)
+    b.load(tmp_path / "gc.vhb")
+    for c in (a, b):
+        c.fuse_frame(pose, v, n, df)
+    ex, _ = compare_blocks(b.block_dict(), a.block_dict())
+    assert ex and b.stats().heapCounter == a.stats().heapCounter
+    r = Context(Config(numVoxelBlocks=512))                  # RefExact: the reference has no working removal
+    assert r.lib.vh_garbage_collect(r._h, 1, 0.0, 0.0, None) == L.VH_ERR_UNSUPPORTED

@@ -30,12 +30,12 @@ __device__ __forceinline__ bool packKey(int x, int y, int z, unsigned long long&
     return true;
 }
 
-__device__ __forceinline__ void finishInsert(const View& v, unsigned slot, int x, int y, int z, bool isArena) {
+__device__ __forceinline__ void finishInsert(const View& v, unsigned slot, int x, int y, int z, bool keepKey) {
     int addr = atomicSub(&v.ctr->heapCounter, 1);           // ref allocSingleBlockInHeap :331
     if (addr < 0) {                                         // heap exhausted: the reference reads out of bounds here (Q6)
         atomicAdd(&v.ctr->heapCounter, 1);
-        // in-bucket slot goes back to free; a linked arena entry stays as a tombstone {key, FREE}
-        v.entries[slot] = isArena ? make_int4(x, y, z, VH_FREE_BLOCK) : freeSlot();
+        // a never-used in-bucket slot goes back to free; a linked arena entry or a reclaimed slot stays a tombstone {key, FREE}
+        v.entries[slot] = keepKey ? make_int4(x, y, z, VH_FREE_BLOCK) : freeSlot();
         atomicAdd(&v.ctr->dropped, 1);
         return;
     }
@@ -45,47 +45,76 @@ __device__ __forceinline__ void finishInsert(const View& v, unsigned slot, int x
     atomicAdd(&v.ctr->lastInserted, 1);
 }
 
+// Slot states: never used {INT_MAX^3, FREE}; live {key, ptr}; being inserted {key, LOCKED}; tombstone {old key, FREE}
+// (left by garbage collection, k_gc.cu, or by an insert that found the heap empty).  Never-used and tombstone slots
+// are both claimable with one 128-bit CAS.  A key is placed in the FIRST claimable slot of its bucket-then-chain scan
+// order, and only after the scan has shown the key is not stored further on -- so concurrent requests for one key
+// always meet at the same slot, and a reused tombstone can never sit in front of a live copy of the same key.
+// Slots fill in scan order, so a never-used slot ends the scan: nothing was ever stored behind it.
 __device__ void insertFixed(const View& v, int x, int y, int z) {
     const unsigned h = bucketOf(v, x, y, z);
     const unsigned base = h * v.bucketSize;
     const int4 want = make_int4(x, y, z, VH_LOCKED_BLOCK);
-    for (unsigned i = 0; i < v.bucketSize; ++i) {
-        int4 e = ldSlot(v.entries + base + i);
-        if (e.w != VH_FREE_BLOCK) {
-            if (sameKey(e, x, y, z)) return;                // present (or being inserted by a peer)
-            continue;
+    for (int attempt = 0; attempt < 64; ++attempt) {
+        int claim = -1;
+        int4 claimSeen = freeSlot();
+        bool ended = false;                                 // hit a never-used slot: end of everything stored
+        for (unsigned i = 0; i < v.bucketSize && !ended; ++i) {
+            const int4 e = ldSlot(v.entries + base + i);
+            if (e.w != VH_FREE_BLOCK) {
+                if (sameKey(e, x, y, z)) return;            // present (or being inserted by a peer)
+                continue;
+            }
+            if (claim < 0) { claim = (int)(base + i); claimSeen = e; }
+            ended = e.x == VH_FREE_COORD;
         }
-        int4 old;
-        if (casSlot(v.entries + base + i, e, want, old)) { finishInsert(v, base + i, x, y, z, false); return; }
-        if (old.w != VH_FREE_BLOCK && sameKey(old, x, y, z)) return;   // a peer won the slot with the same key
-        if (old.w == VH_FREE_BLOCK) --i;                    // slot changed but is still free (rollback): retry it
-    }
-    // bucket full: walk / extend the overflow chain hanging off the bucket's last slot
-    unsigned cur = base + v.bucketSize - 1;
-    unsigned len = 0;
-    int mySlot = -1;
-    while (true) {
-        int off = *reinterpret_cast<volatile int*>(v.chain + cur);
-        if (off != 0) {
-            cur += (unsigned)off;
+        unsigned cur = base + v.bucketSize - 1;
+        unsigned len = 0;
+        bool chainFull = false;
+        if (!ended) {                                       // bucket full of live / tombstone slots: walk the overflow chain
+            while (true) {
+                const int off = *reinterpret_cast<volatile int*>(v.chain + cur);
+                if (off == 0) break;
+                cur += (unsigned)off;
+                ++len;
+                const int4 e = ldSlot(v.entries + cur);
+                if (e.w != VH_FREE_BLOCK) {
+                    if (sameKey(e, x, y, z)) return;
+                } else if (claim < 0) { claim = (int)cur; claimSeen = e; }
+            }
+            chainFull = len >= v.chainMax;
+        }
+        if (claim >= 0) {
+            int4 old;
+            if (casSlot(v.entries + claim, claimSeen, want, old)) {
+                finishInsert(v, (unsigned)claim, x, y, z, claimSeen.x != VH_FREE_COORD || (unsigned)claim >= v.numSlots);
+                return;
+            }
+            if (old.w != VH_FREE_BLOCK && sameKey(old, x, y, z)) return;   // a peer won the slot with the same key
+            continue;                                       // someone else's key took it: rescan
+        }
+        // nothing claimable: extend the chain with a fresh arena slot (lock-free append, CAS on the tail's link)
+        if (chainFull) { atomicAdd(&v.ctr->dropped, 1); return; }
+        const int a = atomicAdd(&v.ctr->overflowUsed, 1);
+        if (a >= (int)v.overflowSlots) { atomicSub(&v.ctr->overflowUsed, 1); atomicAdd(&v.ctr->dropped, 1); return; }
+        const int mySlot = (int)(v.numSlots + (unsigned)a);
+        v.entries[mySlot] = want;
+        __threadfence();                                    // entry visible before it can be reached through the link
+        while (true) {
+            const int prev = atomicCAS(v.chain + cur, 0, mySlot - (int)cur);
+            if (prev == 0) { finishInsert(v, (unsigned)mySlot, x, y, z, true); return; }
+            // a peer appended first: step onto its entry and try again behind it
+            cur += (unsigned)prev;
             ++len;
-            int4 e = ldSlot(v.entries + cur);
-            if (sameKey(e, x, y, z) && e.w != VH_FREE_BLOCK) break;   // present; mySlot (if any) is orphaned below
-            continue;
+            const int4 e = ldSlot(v.entries + cur);
+            if ((e.w != VH_FREE_BLOCK && sameKey(e, x, y, z)) || len >= v.chainMax) {
+                if (!(e.w != VH_FREE_BLOCK && sameKey(e, x, y, z))) atomicAdd(&v.ctr->dropped, 1);
+                v.entries[mySlot] = make_int4(x, y, z, VH_FREE_BLOCK);     // never linked: invisible, leaked
+                return;
+            }
         }
-        if (len >= v.chainMax) { atomicAdd(&v.ctr->dropped, 1); break; }
-        if (mySlot < 0) {
-            int a = atomicAdd(&v.ctr->overflowUsed, 1);
-            if (a >= (int)v.overflowSlots) { atomicSub(&v.ctr->overflowUsed, 1); atomicAdd(&v.ctr->dropped, 1); return; }
-            mySlot = (int)(v.numSlots + (unsigned)a);
-            v.entries[mySlot] = want;
-            __threadfence();                                // entry visible before it can be reached through the link
-        }
-        int prev = atomicCAS(v.chain + cur, 0, mySlot - (int)cur);
-        if (prev == 0) { finishInsert(v, (unsigned)mySlot, x, y, z, true); return; }
-        // a peer appended first: keep walking from its entry with the same arena slot in hand
     }
-    if (mySlot >= 0) v.entries[mySlot] = make_int4(x, y, z, VH_FREE_BLOCK);   // never linked: invisible, leaked
+    atomicAdd(&v.ctr->dropped, 1);                          // 64 lost races in a row: give up on this request
 }
 
 __device__ void insertRefExact(const View& v, int x, int y, int z) {

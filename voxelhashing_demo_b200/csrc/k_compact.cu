@@ -18,8 +18,9 @@ __global__ void __launch_bounds__(256) k_compact(View v) {
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
     const int N = (int)v.numVoxelBlocks;
-    // ids in use are (heapCounter, N-1]; clamp for the exhausted-heap case
-    int first = v.ctr->heapCounter + 1;
+    // ids ever handed out are (min(heapLow, heapCounter), N-1] (garbage collection pushes ids back, so the live
+    // ones are no longer a dense range: blockInfo.w < 0 marks the released ones); clamp for the exhausted-heap case
+    int first = min(v.ctr->heapLow, v.ctr->heapCounter) + 1;
     if (first < 0) first = 0;
     const int stride = gridDim.x * blockDim.x;
     // round the loop so whole warps stay converged for the ballot

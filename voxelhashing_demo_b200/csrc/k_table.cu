@@ -21,6 +21,7 @@ __global__ void k_reset(View v) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         Counters c{};
         c.heapCounter = (int)v.numVoxelBlocks - 1;   // ref :207
+        c.heapLow = c.heapCounter;
         *v.ctr = c;
     }
 }

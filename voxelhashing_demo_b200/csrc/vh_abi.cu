@@ -1,5 +1,6 @@
 // vh_abi.cu -- the extern "C" surface of libvh_b200.so (include/vh/abi.h): context management,
 // the stream-ordered handle API and the reference's legacy entry points on a global context.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -276,6 +277,17 @@ int vh_get_stats(vh_context* c, vh_stats* out, vh_stream s) {
     out->dropped = h.dropped;
     out->numUpdated = h.numUpdated;
     out->lastInserted = h.lastInserted;
+    out->lastFreed = h.gcFreed;
+    return VH_OK;
+}
+
+int vh_garbage_collect(vh_context* c, int scope, float sdf_threshold, float weight_decay, vh_stream s) {
+    if (!c) return fail(VH_ERR_INVALID, "vh_garbage_collect: null context");
+    if (scope != VH_GC_VISIBLE && scope != VH_GC_ALL) return fail(VH_ERR_INVALID, "vh_garbage_collect: unknown scope");
+    if (c->cfg.policy != VH_POLICY_FIXED)
+        return fail(VH_ERR_UNSUPPORTED, "vh_garbage_collect: the RefExact table has no removal (ref deleteVoxelEntry is dead code)");
+    if (!(sdf_threshold > 0.0f)) sdf_threshold = fmaf(c->v.truncScale, c->v.depthMax, c->v.truncation);
+    VH_CUDA(launch_gc(c, scope, sdf_threshold, weight_decay, S(s)));
     return VH_OK;
 }
 
@@ -431,7 +443,7 @@ int vh_save(vh_context* c, const char* path) {
     VH_CUDA(cudaDeviceSynchronize());
     FILE* f = fopen(path, "wb");
     if (!f) return fail(VH_ERR_INVALID, "vh_save: cannot open file");
-    CkptHeader h{{'V', 'H', 'B', '2', '0', '0', 0, 0}, 1, c->v.numBuckets, c->v.bucketSize, c->v.numVoxelBlocks, c->v.overflowSlots,
+    CkptHeader h{{'V', 'H', 'B', '2', '0', '0', 0, 0}, 2, c->v.numBuckets, c->v.bucketSize, c->v.numVoxelBlocks, c->v.overflowSlots,
                  (unsigned)c->cfg.policy, c->v.voxelSize};
     Counters ctr;
     cudaMemcpy(&ctr, c->v.ctr, sizeof(ctr), cudaMemcpyDeviceToHost);
@@ -445,7 +457,7 @@ int vh_save(vh_context* c, const char* path) {
     bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(&ctr, sizeof(ctr), 1, f) == 1;
     ok = ok && put(c->v.entries, slots * sizeof(int4)) && put(c->v.chain, slots * sizeof(int)) &&
          put(c->v.heap, N * sizeof(unsigned)) && put(c->v.blockInfo, N * sizeof(int4));
-    int first = ctr.heapCounter + 1;
+    int first = std::min(ctr.heapLow, ctr.heapCounter) + 1;   // ids ever handed out (garbage collection leaves holes)
     if (first < 0) first = 0;
     if (ok && (size_t)first < N) ok = put(c->v.voxels + (size_t)first * 512, (N - first) * 512 * sizeof(Voxel));
     fclose(f);
@@ -458,7 +470,7 @@ int vh_load(vh_context* c, const char* path) {
     CkptHeader h;
     Counters ctr;
     bool ok = fread(&h, sizeof(h), 1, f) == 1 && fread(&ctr, sizeof(ctr), 1, f) == 1;
-    if (!ok || memcmp(h.magic, "VHB200", 6) != 0 || h.numBuckets != c->v.numBuckets || h.bucketSize != c->v.bucketSize ||
+    if (!ok || memcmp(h.magic, "VHB200", 6) != 0 || h.version != 2 || h.numBuckets != c->v.numBuckets || h.bucketSize != c->v.bucketSize ||
         h.numVoxelBlocks != c->v.numVoxelBlocks || h.overflowSlots != c->v.overflowSlots) {
         fclose(f);
         return fail(VH_ERR_INVALID, "vh_load: checkpoint does not match this context's geometry");
@@ -473,7 +485,7 @@ int vh_load(vh_context* c, const char* path) {
     cudaDeviceSynchronize();
     ok = get(c->v.entries, slots * sizeof(int4)) && get(c->v.chain, slots * sizeof(int)) && get(c->v.heap, N * sizeof(unsigned)) &&
          get(c->v.blockInfo, N * sizeof(int4));
-    int first = ctr.heapCounter + 1;
+    int first = std::min(ctr.heapLow, ctr.heapCounter) + 1;
     if (first < 0) first = 0;
     if (ok) ok = cudaMemset(c->v.voxels, 0, N * 512 * sizeof(Voxel)) == cudaSuccess;
     if (ok && (size_t)first < N) ok = get(c->v.voxels + (size_t)first * 512, (N - first) * 512 * sizeof(Voxel));

@@ -35,6 +35,8 @@ struct Counters {
     unsigned int icpTicket;       // last-CTA-done ticket of the ICP reduction
     unsigned int icpSeq;          // sequence number of the fused cross-GPU exchange in the ICP tail
     unsigned long long numUpdated;
+    int heapLow;                  // lowest heapCounter ever reached: block ids <= heapLow were never handed out
+    int gcFreed;                  // blocks released by the last garbage-collection pass
 };
 
 struct FrameParams {
@@ -114,6 +116,7 @@ cudaError_t launch_set_frame_device(vh_context* c, const float* d_pose, const fl
 cudaError_t launch_alloc(vh_context* c, const float4* verts, cudaStream_t s);
 cudaError_t launch_reset_mutex(vh_context* c, cudaStream_t s);
 cudaError_t launch_compact(vh_context* c, cudaStream_t s);
+cudaError_t launch_gc(vh_context* c, int scope, float sdfThreshold, float weightDecay, cudaStream_t s);
 cudaError_t launch_integrate(vh_context* c, const float4* verts, const float* depthf, int countOverride, cudaStream_t s);
 cudaError_t launch_preprocess(vh_context* c, const uint16_t* depth, float4* verts, float4* normals, float* depthf, cudaStream_t s);
 cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,

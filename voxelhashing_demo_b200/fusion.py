@@ -186,6 +186,11 @@ class Context:
         L.check(self.lib.vh_get_stats(self._h, C.byref(s), _stream(stream)), "vh_get_stats")
         return s
 
+    def garbage_collect(self, scope=L.VH_GC_VISIBLE, sdf_threshold=0.0, weight_decay=0.0, stream=None):
+        """Starve + release blocks (Niessner 2013, 4.4); empties the visible list, so compact again before integrating."""
+        L.check(self.lib.vh_garbage_collect(self._h, int(scope), float(sdf_threshold), float(weight_decay), _stream(stream)),
+                "vh_garbage_collect")
+
     # -- tracking -----------------------------------------------------------------------------------
     def icp_reset(self, reset_estimate=True, stream=None):
         L.check(self.lib.vh_icp_reset(self._h, int(reset_estimate), _stream(stream)))
