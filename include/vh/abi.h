@@ -199,6 +199,19 @@ int vh_get_stats(vh_context* ctx, vh_stats* out, vh_stream s);
 #define VH_GC_VISIBLE 0
 #define VH_GC_ALL 1
 int vh_garbage_collect(vh_context* ctx, int scope, float sdf_threshold, float weight_decay, vh_stream s);
+/* Streaming of the model in and out of the device (Fixed policy; Niessner et al. 2013, section 4.5).
+ * vh_stream_out moves every allocated block whose centre lies farther than `radius` metres from `center_xyz` (world
+ * frame) into the caller's buffers and releases it like vh_garbage_collect does: entries_out[i] = {pos, ptr = 512 * i,
+ * offset = 0} in the reference's 20-byte VoxelEntry layout, voxels_out[512 * i ...] its 512 voxels.  At most
+ * `capacity` blocks move; the rest stay where they are.  *h_count receives the number moved (the call synchronises).
+ * vh_stream_in inserts `count` such blocks again: a key that is absent gets the voxels as they are, a key that was
+ * re-observed meanwhile is merged, sdf = (s1 w1 + s2 w2) / (w1 + w2), w = min(wMax, w1 + w2).  *h_count (may be
+ * NULL) receives the number accepted; blocks the table or heap cannot take are counted in vh_stats.dropped.
+ * The buffers must be device-ACCESSIBLE: device memory, or pinned host memory (cudaHostAlloc), in which case the
+ * blocks travel straight over the host link.  Both calls empty the visible list. */
+int vh_stream_out(vh_context* ctx, const float* center_xyz, float radius, VoxelEntry* entries_out, Voxel* voxels_out,
+                  int capacity, int* h_count, vh_stream s);
+int vh_stream_in(vh_context* ctx, const VoxelEntry* entries, const Voxel* voxels, int count, int* h_count, vh_stream s);
 
 /* ---- tracking (ref CameraTracking.cpp:26-69, Solver.cpp:48-124) ------------------------ */
 /* One fused Gauss-Newton iteration on the device: association + residual + 27-sum reduction

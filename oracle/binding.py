@@ -76,6 +76,10 @@ def oracle_lib() -> C.CDLL:
     lib.vo_compact.restype = I
     lib.vo_garbage_collect.argtypes = [P, I, C.c_float, C.c_float]
     lib.vo_garbage_collect.restype = I
+    lib.vo_stream_out.argtypes = [P, P, C.c_float, P, P, I]
+    lib.vo_stream_out.restype = I
+    lib.vo_stream_in.argtypes = [P, P, P, I]
+    lib.vo_stream_in.restype = I
     lib.vo_integrate.argtypes = [P, P, P]
     lib.vo_integrate.restype = C.c_longlong
     lib.vo_integrate_depthf.argtypes = [P, P, P]
@@ -205,6 +209,19 @@ class OracleTable:
 
     def garbage_collect(self, scope=0, sdf_threshold=0.0, weight_decay=0.0) -> int:
         return int(self.lib.vo_garbage_collect(self.h, int(scope), float(sdf_threshold), float(weight_decay)))
+
+    def stream_out(self, center, radius, capacity):
+        """-> (entries [n,5] int32, voxels [n,512,2] float32) of the blocks farther than radius from center; they leave the table."""
+        ent = np.zeros((max(capacity, 1), 5), np.int32)
+        vox = np.zeros((max(capacity, 1), 512, 2), np.float32)
+        c = f32(center).reshape(3)
+        n = int(self.lib.vo_stream_out(self.h, c.ctypes.data, float(radius), ent.ctypes.data, vox.ctypes.data, int(capacity)))
+        return ent[:n].copy(), vox[:n].copy()
+
+    def stream_in(self, entries, voxels) -> int:
+        ent = np.ascontiguousarray(entries, np.int32).reshape(-1, 5)
+        vox = np.ascontiguousarray(voxels, np.float32)
+        return int(self.lib.vo_stream_in(self.h, ent.ctypes.data, vox.ctypes.data, len(ent)))
 
     def fuse_frame(self, pose, verts, depthf=None):
         rep = self.alloc(pose, verts)

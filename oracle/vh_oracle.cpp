@@ -702,6 +702,60 @@ int vo_garbage_collect(vo_table* t, int scope, float sdfThreshold, float weightD
     return freed;
 }
 
+// ---- streaming (k_gc.cu k_stream_out / k_alloc.cu k_stream_in; Niessner et al. 2013, section 4.5) ------------
+// entries5: x, y, z, ptr (= 512 * record index in voxelsOut), offset (0).  Returns the number of blocks moved.
+int vo_stream_out(vo_table* t, const float* center, float radius, int* entries5, float* voxelsOut, int capacity) {
+    const vo_config& c = t->cfg;
+    const float r2 = radius * radius;
+    int n = 0;
+    for (Entry& e : t->table) {
+        if (e.ptr == kFree || n >= capacity) continue;
+        float dx = ((float)(e.pos.x * 8) + 3.5f) * c.voxelSize - center[0];
+        float dy = ((float)(e.pos.y * 8) + 3.5f) * c.voxelSize - center[1];
+        float dz = ((float)(e.pos.z * 8) + 3.5f) * c.voxelSize - center[2];
+        if (!(dx * dx + dy * dy + dz * dz > r2)) continue;
+        float* vox = t->voxels + (size_t)e.ptr * 2;
+        std::memcpy(voxelsOut + (size_t)n * 1024, vox, sizeof(float) * 1024);
+        int* o = entries5 + (size_t)n * 5;
+        o[0] = e.pos.x; o[1] = e.pos.y; o[2] = e.pos.z; o[3] = n * 512; o[4] = 0;
+        std::memset(vox, 0, sizeof(float) * 1024);
+        t->heap[++t->heapCounter] = (unsigned)(e.ptr / 512);
+        e.ptr = kFree;
+        ++n;
+    }
+    t->compact.clear();
+    return n;
+}
+// Returns the number of blocks accepted (inserted or merged).
+int vo_stream_in(vo_table* t, const int* entries5, const float* voxels, int count) {
+    const vo_config& c = t->cfg;
+    int accepted = 0;
+    for (int b = 0; b < count; ++b) {
+        const int* in = entries5 + (size_t)b * 5;
+        I3 key{in[0], in[1], in[2]};
+        if (c.partCount > 1 && (int)ownerOf(key, c.partCount) != c.partRank) continue;
+        int r = insertFixed(t, key);
+        if (r < 0) continue;
+        const Entry* e = findEntry(t, key);
+        if (!e) continue;
+        float* dst = t->voxels + (size_t)e->ptr * 2;
+        const float* src = voxels + (size_t)in[3] * 2;
+        if (r == 1) std::memcpy(dst, src, sizeof(float) * 1024);
+        else {
+            for (int k = 0; k < 512; ++k) {
+                float w1 = dst[2 * k + 1], w2 = src[2 * k + 1], wn = w1 + w2;
+                if (wn > 0.0f) {
+                    dst[2 * k] = fmaf(dst[2 * k], w1, src[2 * k] * w2) * (1.0f / wn);
+                    dst[2 * k + 1] = fminf(c.integrationWeightMax, wn);
+                } else { dst[2 * k] = 0.0f; dst[2 * k + 1] = 0.0f; }
+            }
+        }
+        ++accepted;
+    }
+    t->compact.clear();
+    return accepted;
+}
+
 // ---- export ---------------------------------------------------------------------------------------
 int vo_num_allocated(vo_table* t) {
     int n = 0;

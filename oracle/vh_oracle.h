@@ -87,6 +87,10 @@ long long vo_integrate_depthf(vo_table* t, const float* pose, const float* depth
 /* Starvation + garbage collection (mirror of vh_garbage_collect).  scope 0 = last compaction, 1 = all.  Returns #released. */
 int  vo_garbage_collect(vo_table* t, int scope, float sdfThreshold, float weightDecay);
 
+/* Streaming (mirror of vh_stream_out / vh_stream_in).  entries5: x, y, z, 512 * record index, 0. */
+int  vo_stream_out(vo_table* t, const float* center, float radius, int* entries5, float* voxelsOut, int capacity);
+int  vo_stream_in(vo_table* t, const int* entries5, const float* voxels, int count);
+
 /* Table export. entries: 5 ints each (x,y,z,ptr,offset), allocated entries only. */
 int  vo_num_allocated(vo_table* t);
 int  vo_export_entries(vo_table* t, int* entries5, int cap);

@@ -380,3 +380,31 @@ def test_garbage_collection_semantics(oracle):
     once.fuse_frame(pose, v, df)
     a, b = ot.block_dict(), once.block_dict()
     assert set(a) == set(b) and all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_stream_out_in_roundtrip(oracle):
+    cfg = small_cfg(policy=POLICY_FIXED, numBuckets=1009, numVoxelBlocks=4096, truncation=0.06, overflowSlots=1024)
+    pose = np.eye(4, dtype=np.float32)
+    depth = render(cfg, scenes.scene_S1(), pose)
+    ot = oracle.OracleTable(cfg)
+    v, _, df = ot.preprocess(depth)
+    ot.fuse_frame(pose, v, df)
+    before, h0 = ot.block_dict(), ot.heap_counter()
+    ent, vox = ot.stream_out((0.0, 0.0, 0.0), 2.2, 4096)
+    inside = ot.block_dict()
+    assert 0 < len(ent) < len(before) and len(inside) + len(ent) == len(before) and ot.heap_counter() == h0 + len(ent)
+    centre = lambda k: (np.array(k) * 8 + 3.5) * cfg.voxelSize
+    assert all(np.linalg.norm(centre(k)) <= 2.2 + 1e-5 for k in inside)
+    assert all(np.linalg.norm(centre(tuple(e[:3]))) > 2.2 - 1e-5 for e in ent)
+    for e in ent:
+        assert np.array_equal(vox[e[3] // 512], before[tuple(e[:3])])
+    assert ot.stream_in(ent, vox) == len(ent)
+    back = ot.block_dict()
+    assert set(back) == set(before) and all(np.array_equal(back[k], before[k]) for k in back) and ot.heap_counter() == h0
+    # merge path: stream the same blocks in once more -> weights add, sdf unchanged up to rounding
+    assert ot.stream_in(ent, vox) == len(ent)
+    merged = ot.block_dict()
+    k = tuple(ent[0][:3])
+    w = before[k][:, 1]
+    assert np.array_equal(merged[k][:, 1], np.minimum(cfg.integrationWeightMax, w + w))
+    assert np.max(np.abs(merged[k][:, 0] - before[k][:, 0])) < 1e-6

@@ -771,3 +771,57 @@ def test_garbage_collect_checkpoint_and_policy(built_library, oracle, tmp_path):
     assert ex and b.stats().heapCounter == a.stats().heapCounter
     r = Context(Config(numVoxelBlocks=512))                  # RefExact: the reference has no working removal
     assert r.lib.vh_garbage_collect(r._h, 1, 0.0, 0.0, None) == L.VH_ERR_UNSUPPORTED
+
+
+# ---- streaming in and out of the device -------------------------------------------------
+def _streamed_dict(ent, vox):
+    ent, vox = ent.cpu().numpy(), vox.cpu().numpy()
+    return {tuple(int(x) for x in e[:3]): vox[e[3] // 512] for e in ent}
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_stream_out_in_matches_oracle(built_library, oracle, pinned):
+    cfg = fixed_cfg(numVoxelBlocks=4096, width=160, height=120, fx=517.3 / 4, fy=516.5 / 4, cx=318.6 / 4, cy=255.3 / 4)
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    frames = []
+    for k in (0, 12):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        depth = render(cfg, scenes.scene_S1(), pose)
+        ov, _, odf = ot.preprocess(depth)
+        v, n, df = gpu_preprocess(ctx, depth)
+        frames.append((pose, ov, odf, v, n, df))
+        ot.fuse_frame(pose, ov, odf)
+        ctx.fuse_frame(pose, v, n, df)
+    before = ctx.block_dict()
+    # 1. everything farther than 2.2 m from the origin leaves; same blocks, same bytes as the oracle
+    oent, ovox = ot.stream_out((0.0, 0.0, 0.0), 2.2, 4096)
+    ent, vox = ctx.stream_out((0.0, 0.0, 0.0), 2.2, 4096, pinned_host=pinned)
+    assert ent.is_pinned() == pinned and 0 < len(ent) == len(oent) < len(before)
+    got, want = _streamed_dict(ent, vox), {tuple(int(x) for x in e[:3]): ovox[e[3] // 512] for e in oent}
+    assert set(got) == set(want) and all(np.array_equal(bits(got[k]), bits(want[k])) for k in got)
+    assert all(np.array_equal(bits(got[k]), bits(before[k])) for k in got)
+    assert ctx.stats().numVisible == 0
+    _same_model(ctx, ot)
+    # 2. the camera looks at the region again: some streamed keys are re-allocated with new observations
+    pose, ov, odf, v, n, df = frames[0]
+    ot.fuse_frame(pose, ov, odf)
+    ctx.fuse_frame(pose, v, n, df)
+    _same_model(ctx, ot)
+    reobserved = set(got) & set(ctx.block_dict())
+    assert reobserved and reobserved != set(got)
+    # 3. stream in: absent keys are copied, re-observed keys merged; order of the records must not matter
+    perm = torch.randperm(len(ent), generator=torch.Generator().manual_seed(3))
+    assert ot.stream_in(oent, ovox) == len(oent)
+    assert ctx.stream_in(ent[perm].contiguous() if not pinned else ent[perm].contiguous().pin_memory(), vox) == len(ent)
+    _same_model(ctx, ot)
+    # 4. a buffer too small takes exactly its capacity; nothing is lost, nothing duplicated
+    all_before = ctx.block_dict()
+    ent2, vox2 = ctx.stream_out((0.0, 0.0, 0.0), 0.0, 10, pinned_host=pinned)
+    rest = ctx.block_dict()
+    moved = _streamed_dict(ent2, vox2)
+    assert len(ent2) == 10 and not (set(moved) & set(rest)) and set(moved) | set(rest) == set(all_before)
+    assert all(np.array_equal(bits(moved[k]), bits(all_before[k])) for k in moved)
+    assert ctx.stream_in(ent2, vox2) == 10
+    ex, _ = compare_blocks(ctx.block_dict(), all_before)
+    assert ex

@@ -30,19 +30,20 @@ __device__ __forceinline__ bool packKey(int x, int y, int z, unsigned long long&
     return true;
 }
 
-__device__ __forceinline__ void finishInsert(const View& v, unsigned slot, int x, int y, int z, bool keepKey) {
+__device__ __forceinline__ bool finishInsert(const View& v, unsigned slot, int x, int y, int z, bool keepKey) {
     int addr = atomicSub(&v.ctr->heapCounter, 1);           // ref allocSingleBlockInHeap :331
     if (addr < 0) {                                         // heap exhausted: the reference reads out of bounds here (Q6)
         atomicAdd(&v.ctr->heapCounter, 1);
         // a never-used in-bucket slot goes back to free; a linked arena entry or a reclaimed slot stays a tombstone {key, FREE}
         v.entries[slot] = keepKey ? make_int4(x, y, z, VH_FREE_BLOCK) : freeSlot();
         atomicAdd(&v.ctr->dropped, 1);
-        return;
+        return false;
     }
     unsigned id = v.heap[addr];                             // ref :333
     v.blockInfo[id] = make_int4(x, y, z, (int)slot);
     reinterpret_cast<volatile int*>(v.entries + slot)[3] = (int)(id * 512u);   // ref :449-451 (ptr = id*512)
     atomicAdd(&v.ctr->lastInserted, 1);
+    return true;
 }
 
 // Slot states: never used {INT_MAX^3, FREE}; live {key, ptr}; being inserted {key, LOCKED}; tombstone {old key, FREE}
@@ -51,7 +52,9 @@ __device__ __forceinline__ void finishInsert(const View& v, unsigned slot, int x
 // order, and only after the scan has shown the key is not stored further on -- so concurrent requests for one key
 // always meet at the same slot, and a reused tombstone can never sit in front of a live copy of the same key.
 // Slots fill in scan order, so a never-used slot ends the scan: nothing was ever stored behind it.
-__device__ void insertFixed(const View& v, int x, int y, int z) {
+// Returns the slot the key lives in (already present, or just inserted: fresh = true), -1 when the request was dropped.
+__device__ int insertFixed(const View& v, int x, int y, int z, bool& fresh) {
+    fresh = false;
     const unsigned h = bucketOf(v, x, y, z);
     const unsigned base = h * v.bucketSize;
     const int4 want = make_int4(x, y, z, VH_LOCKED_BLOCK);
@@ -62,7 +65,7 @@ __device__ void insertFixed(const View& v, int x, int y, int z) {
         for (unsigned i = 0; i < v.bucketSize && !ended; ++i) {
             const int4 e = ldSlot(v.entries + base + i);
             if (e.w != VH_FREE_BLOCK) {
-                if (sameKey(e, x, y, z)) return;            // present (or being inserted by a peer)
+                if (sameKey(e, x, y, z)) return (int)(base + i);   // present (or being inserted by a peer)
                 continue;
             }
             if (claim < 0) { claim = (int)(base + i); claimSeen = e; }
@@ -79,7 +82,7 @@ __device__ void insertFixed(const View& v, int x, int y, int z) {
                 ++len;
                 const int4 e = ldSlot(v.entries + cur);
                 if (e.w != VH_FREE_BLOCK) {
-                    if (sameKey(e, x, y, z)) return;
+                    if (sameKey(e, x, y, z)) return (int)cur;
                 } else if (claim < 0) { claim = (int)cur; claimSeen = e; }
             }
             chainFull = len >= v.chainMax;
@@ -87,34 +90,36 @@ __device__ void insertFixed(const View& v, int x, int y, int z) {
         if (claim >= 0) {
             int4 old;
             if (casSlot(v.entries + claim, claimSeen, want, old)) {
-                finishInsert(v, (unsigned)claim, x, y, z, claimSeen.x != VH_FREE_COORD || (unsigned)claim >= v.numSlots);
-                return;
+                fresh = finishInsert(v, (unsigned)claim, x, y, z, claimSeen.x != VH_FREE_COORD || (unsigned)claim >= v.numSlots);
+                return fresh ? claim : -1;
             }
-            if (old.w != VH_FREE_BLOCK && sameKey(old, x, y, z)) return;   // a peer won the slot with the same key
+            if (old.w != VH_FREE_BLOCK && sameKey(old, x, y, z)) return claim;   // a peer won the slot with the same key
             continue;                                       // someone else's key took it: rescan
         }
         // nothing claimable: extend the chain with a fresh arena slot (lock-free append, CAS on the tail's link)
-        if (chainFull) { atomicAdd(&v.ctr->dropped, 1); return; }
+        if (chainFull) { atomicAdd(&v.ctr->dropped, 1); return -1; }
         const int a = atomicAdd(&v.ctr->overflowUsed, 1);
-        if (a >= (int)v.overflowSlots) { atomicSub(&v.ctr->overflowUsed, 1); atomicAdd(&v.ctr->dropped, 1); return; }
+        if (a >= (int)v.overflowSlots) { atomicSub(&v.ctr->overflowUsed, 1); atomicAdd(&v.ctr->dropped, 1); return -1; }
         const int mySlot = (int)(v.numSlots + (unsigned)a);
         v.entries[mySlot] = want;
         __threadfence();                                    // entry visible before it can be reached through the link
         while (true) {
             const int prev = atomicCAS(v.chain + cur, 0, mySlot - (int)cur);
-            if (prev == 0) { finishInsert(v, (unsigned)mySlot, x, y, z, true); return; }
+            if (prev == 0) { fresh = finishInsert(v, (unsigned)mySlot, x, y, z, true); return fresh ? mySlot : -1; }
             // a peer appended first: step onto its entry and try again behind it
             cur += (unsigned)prev;
             ++len;
             const int4 e = ldSlot(v.entries + cur);
             if ((e.w != VH_FREE_BLOCK && sameKey(e, x, y, z)) || len >= v.chainMax) {
-                if (!(e.w != VH_FREE_BLOCK && sameKey(e, x, y, z))) atomicAdd(&v.ctr->dropped, 1);
+                const bool present = e.w != VH_FREE_BLOCK && sameKey(e, x, y, z);
+                if (!present) atomicAdd(&v.ctr->dropped, 1);
                 v.entries[mySlot] = make_int4(x, y, z, VH_FREE_BLOCK);     // never linked: invisible, leaked
-                return;
+                return present ? (int)cur : -1;
             }
         }
     }
     atomicAdd(&v.ctr->dropped, 1);                          // 64 lost races in a row: give up on this request
+    return -1;
 }
 
 __device__ void insertRefExact(const View& v, int x, int y, int z) {
@@ -159,7 +164,8 @@ __device__ __forceinline__ void warpRequest(const View& v, const float* pose, un
     }
     if (P::fixed) {
         if (!ownedHere(v, x, y, z)) return;
-        insertFixed(v, x, y, z);
+        bool fresh;
+        insertFixed(v, x, y, z, fresh);
     } else {
         if (!refBlockInFrustum(v, pose, x, y, z)) return;   // ref :673; depends on (key, pose) only
         insertRefExact(v, x, y, z);
@@ -232,6 +238,68 @@ __global__ void __launch_bounds__(256) k_alloc(View v, const float4* __restrict_
             }
         }
     }
+}
+
+// ---- stream-in: blocks come back from a caller-owned buffer (k_gc.cu: k_stream_out) ---------------------------
+// One CTA per incoming block: thread 0 inserts the key like any allocation request; a fresh block (zeroed) receives
+// the 4 KB as they are, a block that was re-observed in the meantime is merged by the running-average rule
+// sdf = (s1 w1 + s2 w2) / (w1 + w2), w = min(wMax, w1 + w2).
+__global__ void __launch_bounds__(128, 8) k_stream_in(View v, const VoxelEntry* __restrict__ entries, const Voxel* __restrict__ voxels, int count) {
+    __shared__ int sPtr, sFresh, sSrc;
+    for (int b = blockIdx.x; b < count; b += gridDim.x) {
+        if (threadIdx.x == 0) {
+            const VoxelEntry e = entries[b];
+            int ptr = -1;
+            bool fresh = false;
+            if (ownedHere(v, e.pos.x, e.pos.y, e.pos.z)) {
+                const int slot = insertFixed(v, e.pos.x, e.pos.y, e.pos.z, fresh);
+                if (slot >= 0) ptr = ldSlot(v.entries + slot).w;
+            }
+            if (ptr >= 0) atomicAdd(&v.ctr->streamCount, 1);
+            sPtr = ptr;
+            sFresh = fresh;
+            sSrc = e.ptr;                                   // record index * 512 in the caller's voxel buffer
+        }
+        __syncthreads();
+        const int ptr = sPtr;
+        const bool fresh = sFresh != 0;
+        const int srcIdx = sSrc;
+        __syncthreads();
+        if (ptr < 0) continue;
+        const float4* src = reinterpret_cast<const float4*>(voxels + (size_t)srcIdx + threadIdx.x * 4);
+        float4 a = src[0], c = src[1];
+        float in[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        float4* dst = reinterpret_cast<float4*>(v.voxels + (size_t)ptr + threadIdx.x * 4);
+        if (!fresh) {
+            float4 p = dst[0], q = dst[1];
+            float cur[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float w1 = cur[2 * k + 1], w2 = in[2 * k + 1];
+                const float wn = w1 + w2;
+                if (wn > 0.0f) {
+                    in[2 * k] = fmaf(cur[2 * k], w1, in[2 * k] * w2) * __frcp_rn(wn);
+                    in[2 * k + 1] = fminf(v.wMax, wn);
+                } else {
+                    in[2 * k] = 0.0f;
+                    in[2 * k + 1] = 0.0f;
+                }
+            }
+        }
+        dst[0] = make_float4(in[0], in[1], in[2], in[3]);
+        dst[1] = make_float4(in[4], in[5], in[6], in[7]);
+    }
+}
+
+__global__ void k_stream_in_begin(View v) { v.ctr->streamCount = 0; v.ctr->lastInserted = 0; }
+
+cudaError_t launch_stream_in(vh_context* c, const VoxelEntry* entries, const Voxel* voxels, int count, cudaStream_t s) {
+    k_stream_in_begin<<<1, 1, 0, s>>>(c->v);
+    if (count <= 0) return cudaGetLastError();
+    int grid = c->numSMs * 8;
+    if (count < grid) grid = count;
+    k_stream_in<<<grid, 128, 0, s>>>(c->v, entries, voxels, count);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_alloc(vh_context* c, const float4* verts, cudaStream_t s) {

@@ -71,10 +71,7 @@ __global__ void __launch_bounds__(128, 8) k_gc(View v, int scope, float sdfThres
             const bool release = bmx == 0.0f || bmn >= sdfThreshold;
             sFree = release;
             if (release) {
-                v.entries[info.w] = make_int4(info.x, info.y, info.z, VH_FREE_BLOCK);      // tombstone
-                v.blockInfo[id] = make_int4(info.x, info.y, info.z, -1);
-                const int addr = atomicAdd(&v.ctr->heapCounter, 1) + 1;                     // ref removeSingleBlockInHeap :338-339
-                v.heap[addr] = (unsigned)id;
+                releaseBlock(v, id, info);
                 atomicAdd(&v.ctr->gcFreed, 1);
             }
         }
@@ -96,6 +93,65 @@ __global__ void k_gc_begin(View v) {
     c->gcFreed = 0;
 }
 __global__ void k_gc_end(View v) { v.ctr->compactCount = 0; }   // the visible list may name released blocks now
+
+// ---- stream-out: blocks far from the region of interest leave the table for a caller-owned buffer ------------
+// (Niessner et al. 2013, section 4.5: the active region is a sphere around the camera; blocks outside it are moved
+// to host memory and come back through k_stream_in when the sphere reaches them again.)  The buffers only need to be
+// device-ACCESSIBLE: pinned host memory works, the copy then goes straight over the host link.
+__global__ void __launch_bounds__(128, 8) k_stream_out(View v, float cx, float cy, float cz, float radius2, VoxelEntry* entriesOut,
+                                                       Voxel* voxelsOut, int capacity) {
+    __shared__ int sDst;
+    const int N = (int)v.numVoxelBlocks;
+    const int firstId = max(v.ctr->heapLow + 1, 0);
+    for (int id = firstId + blockIdx.x; id < N; id += gridDim.x) {
+        const int4 info = v.blockInfo[id];
+        if (info.w < 0) continue;
+        // centre of the block: voxel indices 8b .. 8b+7 sit at (8b + k) * voxelSize
+        const float dx = ((float)(info.x * 8) + 3.5f) * v.voxelSize - cx;
+        const float dy = ((float)(info.y * 8) + 3.5f) * v.voxelSize - cy;
+        const float dz = ((float)(info.z * 8) + 3.5f) * v.voxelSize - cz;
+        if (!(dx * dx + dy * dy + dz * dz > radius2)) continue;             // CTA-uniform
+        if (threadIdx.x == 0) {
+            int dst = atomicAdd(&v.ctr->streamCount, 1);
+            if (dst >= capacity) { atomicSub(&v.ctr->streamCount, 1); dst = -1; }   // buffer full: the block stays
+            else {
+                VoxelEntry e;
+                e.pos = make_int3(info.x, info.y, info.z);
+                e.ptr = dst * 512;
+                e.offset = 0;
+                entriesOut[dst] = e;
+                releaseBlock(v, id, info);
+            }
+            sDst = dst;
+        }
+        __syncthreads();
+        const int dst = sDst;
+        __syncthreads();
+        if (dst < 0) continue;
+        Voxel* sector = v.voxels + (size_t)id * 512 + threadIdx.x * 4;
+        F8g x = ldSector(sector);
+        float4* out = reinterpret_cast<float4*>(voxelsOut + (size_t)dst * 512 + threadIdx.x * 4);   // may be host memory: plain stores
+        out[0] = make_float4(x.a[0], x.a[1], x.a[2], x.a[3]);
+        out[1] = make_float4(x.a[4], x.a[5], x.a[6], x.a[7]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x.a[k] = 0.0f;
+        stSector(sector, x);
+    }
+}
+
+__global__ void k_stream_begin(View v) {
+    Counters* c = v.ctr;
+    c->heapLow = min(c->heapLow, c->heapCounter);
+    c->streamCount = 0;
+}
+
+cudaError_t launch_stream_out(vh_context* c, const float* center, float radius, VoxelEntry* entriesOut, Voxel* voxelsOut, int capacity,
+                              cudaStream_t s) {
+    k_stream_begin<<<1, 1, 0, s>>>(c->v);
+    k_stream_out<<<c->numSMs * 8, 128, 0, s>>>(c->v, center[0], center[1], center[2], radius * radius, entriesOut, voxelsOut, capacity);
+    k_gc_end<<<1, 1, 0, s>>>(c->v);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_gc(vh_context* c, int scope, float sdfThreshold, float weightDecay, cudaStream_t s) {
     k_gc_begin<<<1, 1, 0, s>>>(c->v);

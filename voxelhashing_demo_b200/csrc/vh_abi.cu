@@ -291,6 +291,30 @@ int vh_garbage_collect(vh_context* c, int scope, float sdf_threshold, float weig
     return VH_OK;
 }
 
+static int readStreamCount(vh_context* c, int* h_count, vh_stream s) {
+    Counters h;
+    VH_CUDA(cudaMemcpyAsync(&h, c->v.ctr, sizeof(h), cudaMemcpyDeviceToHost, S(s)));
+    VH_CUDA(cudaStreamSynchronize(S(s)));
+    if (h_count) *h_count = h.streamCount;
+    return VH_OK;
+}
+int vh_stream_out(vh_context* c, const float* center, float radius, VoxelEntry* entries_out, Voxel* voxels_out, int capacity,
+                  int* h_count, vh_stream s) {
+    if (!c || !center || !h_count || capacity < 0 || (capacity > 0 && (!entries_out || !voxels_out)))
+        return fail(VH_ERR_INVALID, "vh_stream_out: bad argument");
+    if (c->cfg.policy != VH_POLICY_FIXED) return fail(VH_ERR_UNSUPPORTED, "vh_stream_out: the RefExact table has no removal");
+    if (!(radius >= 0.0f)) return fail(VH_ERR_INVALID, "vh_stream_out: radius must be >= 0");
+    VH_CUDA(launch_stream_out(c, center, radius, entries_out, voxels_out, capacity, S(s)));
+    return readStreamCount(c, h_count, s);
+}
+int vh_stream_in(vh_context* c, const VoxelEntry* entries, const Voxel* voxels, int count, int* h_count, vh_stream s) {
+    if (!c || count < 0 || (count > 0 && (!entries || !voxels))) return fail(VH_ERR_INVALID, "vh_stream_in: bad argument");
+    if (c->cfg.policy != VH_POLICY_FIXED) return fail(VH_ERR_UNSUPPORTED, "vh_stream_in: the RefExact table has no removal");
+    VH_CUDA(launch_stream_in(c, entries, voxels, count, S(s)));
+    VH_CUDA(cudaMemsetAsync(&c->v.ctr->compactCount, 0, sizeof(int), S(s)));
+    return readStreamCount(c, h_count, s);
+}
+
 // ---- tracking -------------------------------------------------------------------------------------
 int vh_icp_reset(vh_context* c, int reset_estimate, vh_stream s) {
     if (!c) return fail(VH_ERR_INVALID, "vh_icp_reset: null context");

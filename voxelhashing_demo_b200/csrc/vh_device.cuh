@@ -141,6 +141,17 @@ __device__ __forceinline__ int lookupBlock(const View& v, int x, int y, int z) {
     return VH_FREE_BLOCK;
 }
 
+// Give a block back (garbage collection, stream-out): the hash slot becomes a tombstone {key, FREE} -- chain links
+// stay, lookups and inserts keep walking through it and k_alloc.cu reclaims it --, compaction stops seeing the id,
+// and the id goes back on the heap (ref removeSingleBlockInHeap, VoxelUtils.cu:336-341).  One thread per block;
+// the caller zeroes the 4 KB.
+__device__ __forceinline__ void releaseBlock(const View& v, int id, int4 info) {
+    v.entries[info.w] = make_int4(info.x, info.y, info.z, VH_FREE_BLOCK);
+    v.blockInfo[id] = make_int4(info.x, info.y, info.z, -1);
+    const int addr = atomicAdd(&v.ctr->heapCounter, 1) + 1;
+    v.heap[addr] = (unsigned)id;
+}
+
 __device__ __forceinline__ float warpSum(float x) {
     x += __shfl_xor_sync(0xffffffffu, x, 16);
     x += __shfl_xor_sync(0xffffffffu, x, 8);

@@ -37,6 +37,8 @@ struct Counters {
     unsigned long long numUpdated;
     int heapLow;                  // lowest heapCounter ever reached: block ids <= heapLow were never handed out
     int gcFreed;                  // blocks released by the last garbage-collection pass
+    int streamCount;              // blocks moved by the last stream-out / stream-in pass
+    int pad0;
 };
 
 struct FrameParams {
@@ -117,6 +119,9 @@ cudaError_t launch_alloc(vh_context* c, const float4* verts, cudaStream_t s);
 cudaError_t launch_reset_mutex(vh_context* c, cudaStream_t s);
 cudaError_t launch_compact(vh_context* c, cudaStream_t s);
 cudaError_t launch_gc(vh_context* c, int scope, float sdfThreshold, float weightDecay, cudaStream_t s);
+cudaError_t launch_stream_out(vh_context* c, const float* center, float radius, VoxelEntry* entriesOut, Voxel* voxelsOut, int capacity,
+                              cudaStream_t s);
+cudaError_t launch_stream_in(vh_context* c, const VoxelEntry* entries, const Voxel* voxels, int count, cudaStream_t s);
 cudaError_t launch_integrate(vh_context* c, const float4* verts, const float* depthf, int countOverride, cudaStream_t s);
 cudaError_t launch_preprocess(vh_context* c, const uint16_t* depth, float4* verts, float4* normals, float* depthf, cudaStream_t s);
 cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,

@@ -191,6 +191,29 @@ class Context:
         L.check(self.lib.vh_garbage_collect(self._h, int(scope), float(sdf_threshold), float(weight_decay), _stream(stream)),
                 "vh_garbage_collect")
 
+    def stream_out(self, center, radius, capacity, pinned_host=True, stream=None):
+        """Move the blocks farther than `radius` metres from `center` out of the table (Niessner 2013, 4.5).
+        -> (entries [n,5] int32 tensor, voxels [n,512,2] float32 tensor); in pinned host memory by default, which the
+        kernel writes straight over the host link."""
+        import torch
+
+        cap = max(int(capacity), 1)
+        kw = dict(pin_memory=True) if pinned_host else dict(device="cuda")
+        ent = torch.zeros((cap, 5), dtype=torch.int32, **kw)
+        vox = torch.zeros((cap, 512, 2), dtype=torch.float32, **kw)
+        c3 = (C.c_float * 3)(*[float(x) for x in center])
+        n = C.c_int(0)
+        L.check(self.lib.vh_stream_out(self._h, c3, float(radius), _ptr(ent), _ptr(vox), int(capacity), C.byref(n), _stream(stream)),
+                "vh_stream_out")
+        return ent[: n.value], vox[: n.value]
+
+    def stream_in(self, entries, voxels, stream=None) -> int:
+        """Bring blocks back (device or pinned-host tensors as returned by stream_out); -> number accepted."""
+        n = C.c_int(0)
+        L.check(self.lib.vh_stream_in(self._h, _ptr(entries), _ptr(voxels), int(entries.shape[0]), C.byref(n), _stream(stream)),
+                "vh_stream_in")
+        return n.value
+
     # -- tracking -----------------------------------------------------------------------------------
     def icp_reset(self, reset_estimate=True, stream=None):
         L.check(self.lib.vh_icp_reset(self._h, int(reset_estimate), _stream(stream)))
