@@ -288,7 +288,15 @@ enum vh_track_mode {
     VH_TRACK_FRAME_TO_MODEL = 1,   /* ICP target = raycast of the model at the previous pose (Fixed only) */
     VH_TRACK_NONE = 2              /* no ICP: every frame is fused at the pose set by vh_pipeline_reset */
 };
+/* useGraph is a flag word: VH_PIPE_GRAPH captures the per-frame work into CUDA graphs; VH_PIPE_OVERLAP (needs
+ * VH_PIPE_GRAPH and frame-to-frame tracking, ignored otherwise) additionally runs the fusion of frame k on an internal
+ * stream beside the preprocessing and tracking of frame k+1.  With VH_PIPE_OVERLAP the MODEL lags the pose: after
+ * vh_pipeline_push_* the caller's stream is ordered behind the pose of the frame, not behind its fusion; call
+ * vh_pipeline_flush (or vh_pipeline_pose, which includes it) before reading the table on that stream. */
+#define VH_PIPE_GRAPH 1
+#define VH_PIPE_OVERLAP 2
 int  vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGraph, vh_pipeline** out);
+int  vh_pipeline_flush(vh_pipeline* p, vh_stream s);
 void vh_pipeline_destroy(vh_pipeline* p);
 /* New sequence: frame counter, ICP state and pose (16 floats row-major on the host, NULL = identity).
  * Synchronises. The table itself is reset with vh_reset. */

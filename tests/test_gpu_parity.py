@@ -455,24 +455,30 @@ def test_pipeline_tracks_synthetic_trajectory(built_library, oracle):
     poses = [scenes.trajectory_C2(k) for k in range(40)]
     frames = [cu(render(cfg, scenes.scene_S1T(), p).reshape(-1)) for p in poses]
     results = []
-    for use_graph in (True, False):
+    models = []
+    for use_graph, overlap in ((True, False), (False, False), (True, True)):
         ctx = Context(cfg)
-        pipe = FramePipeline(ctx, iterations=10, mode=FramePipeline.FRAME_TO_FRAME, use_graph=use_graph)
+        pipe = FramePipeline(ctx, iterations=10, mode=FramePipeline.FRAME_TO_FRAME, use_graph=use_graph, overlap=overlap)
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
             pipe.reset(poses[0].astype(np.float32))
             for f in frames:
                 pipe.push_device(f)
             pose = pipe.pose()
-        st = ctx.stats()
+            st = ctx.stats(s)
         results.append((pose, st.numAllocated, int(st.numUpdated), pipe.launches()))
+        models.append(ctx.block_dict())
         truth = poses[-1]
         assert rot_err(pose[:3, :3], truth[:3, :3]) < 5e-3
         assert np.max(np.abs(pose[:3, 3] - truth[:3, 3])) < 0.01
         assert st.numAllocated > 300 and st.dropped == 0
-    assert np.array_equal(bits(results[0][0]), bits(results[1][0]))
-    assert results[0][1:3] == results[1][1:3]
-    assert results[0][3] == results[1][3] == 40 + 39 * (10 + 1) + 40 * 3 + 1
+    for r in results[1:]:                                   # plain launches and the overlapped schedule: same bits
+        assert np.array_equal(bits(results[0][0]), bits(r[0]))
+        assert results[0][1:3] == r[1:3]
+        assert results[0][3] == r[3] == 40 + 39 * (10 + 1) + 40 * 3 + 1
+    for m in models[1:]:
+        exact, _ = compare_blocks(m, models[0])
+        assert exact
 
 
 def test_frame_to_model_tracking(built_library, oracle):

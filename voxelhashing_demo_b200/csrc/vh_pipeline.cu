@@ -35,6 +35,14 @@ struct vh_pipeline {
     cudaGraph_t graph[2];
     cudaGraphExec_t exec[2];
     bool haveGraph[2];
+    // overlapped schedule (VH_PIPE_OVERLAP): fusion of frame k runs on its own stream beside preprocess + ICP of frame k+1
+    bool overlap;
+    cudaStream_t fuseStream;
+    cudaEvent_t evPose, evFused;
+    bool fusePending;              // evFused has been recorded and not yet waited for by the caller's stream
+    cudaGraph_t fuseGraph[2];
+    cudaGraphExec_t fuseExec[2];
+    bool haveFuseGraph[2];
 };
 
 namespace {
@@ -46,6 +54,32 @@ int pfail(int code, const char* what, cudaError_t e = cudaSuccess) {
     return code;
 }
 #define PCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return pfail(VH_ERR_CUDA, #expr, _e); } while (0)
+
+cudaError_t enqueueIcp(vh_pipeline* p, int par, cudaStream_t s, int* n) {
+    vh_context* c = p->ctx;
+    const float4* tg = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelVerts : p->verts[1 - par];
+    const float4* tgN = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelNormals : p->normals[1 - par];
+    for (int it = 0; it < p->iterations; ++it) {                           // CameraTracking.cpp:35
+        cudaError_t e = launch_icp_iter_ex(c, p->verts[par], p->normals[par], tg, tgN, 0, c->v.H, nullptr, true, it == 0, it > 0, s);
+        if (e != cudaSuccess) return e;
+    }
+    *n = p->iterations;
+    return cudaSuccess;
+}
+cudaError_t enqueueFusion(vh_pipeline* p, int par, cudaStream_t s, int* n) {
+    vh_context* c = p->ctx;
+    cudaError_t e;
+    int k = 0;
+    if (c->cfg.policy == VH_POLICY_REF_EXACT) { e = launch_reset_mutex(c, s); if (e != cudaSuccess) return e; ++k; }
+    e = launch_alloc(c, p->verts[par], s);                                 // SDF_Hashtable.cpp:27
+    if (e != cudaSuccess) return e;
+    e = launch_compact(c, s);                                              // :30
+    if (e != cudaSuccess) return e;
+    e = launch_integrate(c, p->verts[par], c->cfg.policy == VH_POLICY_FIXED ? p->depthf[par] : nullptr, -1, s);   // :36
+    if (e != cudaSuccess) return e;
+    *n = k + 3;
+    return cudaSuccess;
+}
 
 // the tracked part of a frame (everything after preprocess); returns kernels launched via *n
 cudaError_t enqueueBody(vh_pipeline* p, int par, bool track, cudaStream_t s, int* n) {
@@ -97,7 +131,9 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
     p->ctx = ctx;
     p->iterations = icpIterations > 0 ? icpIterations : ctx->cfg.icpIterations;
     p->mode = mode;
-    p->useGraph = useGraph != 0;
+    p->useGraph = (useGraph & VH_PIPE_GRAPH) != 0;
+    // the overlapped schedule needs a model-independent ICP target (frame-to-frame) and the graph path
+    p->overlap = (useGraph & VH_PIPE_OVERLAP) != 0 && p->useGraph && mode == VH_TRACK_FRAME_TO_FRAME;
     const size_t px = (size_t)ctx->v.W * ctx->v.H;
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
@@ -110,6 +146,11 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
         chk(cudaMalloc((void**)&p->d_depthStage[i], px * sizeof(uint16_t)));
         chk(cudaEventCreateWithFlags(&p->evCopied[i], cudaEventDisableTiming));
         chk(cudaEventCreateWithFlags(&p->evConsumed[i], cudaEventDisableTiming));
+    }
+    if (p->overlap) {
+        chk(cudaStreamCreateWithFlags(&p->fuseStream, cudaStreamNonBlocking));
+        chk(cudaEventCreateWithFlags(&p->evPose, cudaEventDisableTiming));
+        chk(cudaEventCreateWithFlags(&p->evFused, cudaEventDisableTiming));
     }
     if (mode == VH_TRACK_FRAME_TO_MODEL) {
         chk(cudaMalloc((void**)&p->modelVerts, px * sizeof(float4)));
@@ -126,11 +167,15 @@ void vh_pipeline_destroy(vh_pipeline* p) {
     if (!p) return;
     for (int i = 0; i < 2; ++i) {
         if (p->haveGraph[i]) { cudaGraphExecDestroy(p->exec[i]); cudaGraphDestroy(p->graph[i]); }
+        if (p->haveFuseGraph[i]) { cudaGraphExecDestroy(p->fuseExec[i]); cudaGraphDestroy(p->fuseGraph[i]); }
         cudaFree(p->verts[i]); cudaFree(p->normals[i]); cudaFree(p->depthf[i]); cudaFree(p->d_depthStage[i]);
         if (p->evCopied[i]) cudaEventDestroy(p->evCopied[i]);
         if (p->evConsumed[i]) cudaEventDestroy(p->evConsumed[i]);
     }
     if (p->copyStream) cudaStreamDestroy(p->copyStream);
+    if (p->fuseStream) { cudaStreamSynchronize(p->fuseStream); cudaStreamDestroy(p->fuseStream); }
+    if (p->evPose) cudaEventDestroy(p->evPose);
+    if (p->evFused) cudaEventDestroy(p->evFused);
     cudaFree(p->modelVerts); cudaFree(p->modelNormals); cudaFree(p->d_pose);
     delete p;
 }
@@ -140,6 +185,8 @@ int vh_pipeline_reset(vh_pipeline* p, const float* pose16_host, vh_stream s) {
     if (!p) return pfail(VH_ERR_INVALID, "vh_pipeline_reset: null pipeline");
     const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+    if (p->fuseStream) PCUDA(cudaStreamSynchronize(p->fuseStream));
+    p->fusePending = false;
     PCUDA(cudaStreamSynchronize(st));
     PCUDA(cudaMemcpy(p->d_pose, pose16_host ? pose16_host : ident, 16 * sizeof(float), cudaMemcpyHostToDevice));
     PCUDA(launch_icp_reset(p->ctx, true, st));
@@ -156,7 +203,37 @@ static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, c
     const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
     int n = 0;
     const int slot = p->mode == VH_TRACK_FRAME_TO_MODEL ? 0 : par;
-    if (track && p->useGraph && st != nullptr) {
+    if (p->overlap && st != nullptr) {
+        // caller's stream:  preprocess(k) -> ICP(k) x iterations -> [wait fusion(k-1)] -> pose_k, frame constants
+        // fusion stream:    [wait pose_k] -> alloc(k) -> compact -> integrate(k)
+        // The next push puts preprocess(k+1) + ICP(k+1) on the caller's stream right behind pose_k, beside fusion(k):
+        // the single-CTA tail of every ICP iteration (reduction + 6x6 solve) leaves the other SMs to the fusion kernels.
+        auto captured = [&](cudaStream_t cs, bool icp, cudaGraph_t* g, cudaGraphExec_t* ex, bool* have, int* cnt) -> int {
+            if (!*have) {
+                PCUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+                cudaError_t e = icp ? enqueueIcp(p, par, cs, cnt) : enqueueFusion(p, par, cs, cnt);
+                cudaError_t e2 = cudaStreamEndCapture(cs, g);
+                if (e != cudaSuccess) return pfail(VH_ERR_CUDA, "pipeline capture", e);
+                if (e2 != cudaSuccess) return pfail(VH_ERR_CUDA, "cudaStreamEndCapture", e2);
+                PCUDA(cudaGraphInstantiate(ex, *g, 0));
+                *have = true;
+            } else {
+                *cnt = icp ? p->iterations : 3 + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
+            }
+            PCUDA(cudaGraphLaunch(*ex, cs));
+            return VH_OK;
+        };
+        int nIcp = 0, nFuse = 0;
+        if (track) { int rc = captured(st, true, &p->graph[par], &p->exec[par], &p->haveGraph[par], &nIcp); if (rc != VH_OK) return rc; }
+        if (p->fusePending) PCUDA(cudaStreamWaitEvent(st, p->evFused, 0));   // frame constants / counters are about to change
+        PCUDA(launch_set_frame_device(c, p->d_pose, track ? c->icp->delta : nullptr, track ? p->d_pose : nullptr, st));
+        PCUDA(cudaEventRecord(p->evPose, st));
+        PCUDA(cudaStreamWaitEvent(p->fuseStream, p->evPose, 0));
+        { int rc = captured(p->fuseStream, false, &p->fuseGraph[par], &p->fuseExec[par], &p->haveFuseGraph[par], &nFuse); if (rc != VH_OK) return rc; }
+        PCUDA(cudaEventRecord(p->evFused, p->fuseStream));
+        p->fusePending = true;
+        n = nIcp + 1 + nFuse;
+    } else if (track && p->useGraph && st != nullptr) {
         // frame-to-model always reads maps[par] too, so keep one graph per parity in both modes
         if (!p->haveGraph[par]) {
             PCUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -205,9 +282,17 @@ int vh_pipeline_push_host(vh_pipeline* p, const uint16_t* h_depth, float* h_pose
     return VH_OK;
 }
 
+// Overlapped schedule only: make stream s wait for the fusion of the latest pushed frame (a no-op otherwise).
+int vh_pipeline_flush(vh_pipeline* p, vh_stream s) {
+    if (!p) return pfail(VH_ERR_INVALID, "vh_pipeline_flush: null pipeline");
+    if (p->fusePending) PCUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(s), p->evFused, 0));
+    return VH_OK;
+}
+
 int vh_pipeline_pose(vh_pipeline* p, float* pose16, vh_stream s) {
     if (!p || !pose16) return pfail(VH_ERR_INVALID, "vh_pipeline_pose: null argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+    if (p->fusePending) PCUDA(cudaStreamWaitEvent(st, p->evFused, 0));
     PCUDA(cudaMemcpyAsync(pose16, p->d_pose, 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
     PCUDA(cudaStreamSynchronize(st));
     return VH_OK;

@@ -357,11 +357,17 @@ class FramePipeline:
 
     FRAME_TO_FRAME, FRAME_TO_MODEL, NONE = 0, 1, 2
 
-    def __init__(self, ctx: Context, iterations: int = 0, mode: int = 0, use_graph: bool = True):
+    def __init__(self, ctx: Context, iterations: int = 0, mode: int = 0, use_graph: bool = True, overlap: bool = False):
+        """overlap=True (frame-to-frame + graphs only): the fusion of frame k runs beside the tracking of frame k+1;
+        the model then lags the pose until flush() / pose()."""
         self.ctx = ctx
         self.lib = ctx.lib
         self._p = C.c_void_p()
-        L.check(self.lib.vh_pipeline_create(ctx.handle, iterations, mode, int(use_graph), C.byref(self._p)), "vh_pipeline_create")
+        flags = (L.VH_PIPE_GRAPH if use_graph else 0) | (L.VH_PIPE_OVERLAP if overlap else 0)
+        L.check(self.lib.vh_pipeline_create(ctx.handle, iterations, mode, flags, C.byref(self._p)), "vh_pipeline_create")
+
+    def flush(self, stream=None):
+        L.check(self.lib.vh_pipeline_flush(self._p, _stream(stream)), "vh_pipeline_flush")
 
     def close(self):
         if getattr(self, "_p", None) is not None and self._p:

@@ -15,6 +15,7 @@ LIB_PATH = _PKG / "libvh_b200.so"
 
 VH_OK, VH_ERR_INVALID, VH_ERR_CUDA, VH_ERR_NO_DEVICE, VH_ERR_CAPACITY, VH_ERR_UNSUPPORTED = range(6)
 VH_GC_VISIBLE, VH_GC_ALL = 0, 1
+VH_PIPE_GRAPH, VH_PIPE_OVERLAP = 1, 2
 POLICY_REF_EXACT, POLICY_FIXED = 0, 1
 
 
@@ -105,7 +106,7 @@ HANDLE_SYMBOLS = [
     "vh_jacobians", "vh_raycast", "vh_export_entries", "vh_export_compact", "vh_export_block",
     "vh_compact_table_device", "vh_compact_counter_device", "vh_voxel_blocks_device", "vh_save", "vh_load",
     "vh_dump_text",
-    "vh_pipeline_create", "vh_pipeline_destroy", "vh_pipeline_reset", "vh_pipeline_push_device",
+    "vh_pipeline_create", "vh_pipeline_flush", "vh_pipeline_destroy", "vh_pipeline_reset", "vh_pipeline_push_device",
     "vh_pipeline_push_host", "vh_pipeline_pose", "vh_pipeline_pose_device", "vh_pipeline_maps", "vh_pipeline_launches",
 ]
 
@@ -177,6 +178,7 @@ def load_library() -> C.CDLL:
     lib.vh_dump_text.argtypes = [P, C.c_char_p]
     # native frame pipeline
     lib.vh_pipeline_create.argtypes = [P, I, I, I, C.POINTER(P)]
+    lib.vh_pipeline_flush.argtypes = [P, P]
     lib.vh_pipeline_destroy.argtypes = [P]
     lib.vh_pipeline_destroy.restype = None
     lib.vh_pipeline_reset.argtypes = [P, P, P]
