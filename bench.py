@@ -368,6 +368,17 @@ def integrate_hbm_roofline(stream):
             if i >= 3:
                 times.append(e0.elapsed_time(e1) * 1e-3)
         st = ctx.stats(stream)
+        # garbage-collection scan of the same model (read-only here: no ageing, nothing qualifies for release)
+        gc_times = []
+        for i in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.garbage_collect(1, 0.0, 0.0, stream)
+            e1.record(stream)
+            stream.synchronize()
+            if i >= 2:
+                gc_times.append(e0.elapsed_time(e1) * 1e-3)
+        freed = ctx.stats(stream).lastFreed
     peak, which = peaks()
     n = cfg.width * cfg.height
     nbytes = 16 * int(st.numUpdated) + 16 * st.numVisible + 4 * n
@@ -378,6 +389,9 @@ def integrate_hbm_roofline(stream):
             "peak_source": which, "us": t * 1e6,
             "visible_blocks": st.numVisible, "voxel_working_set_MB": st.numVisible * 4096 / 1e6, "voxels_updated": int(st.numUpdated),
             "voxel_updates_per_s": int(st.numUpdated) / t,
+            "gc_scan": {"kernel": "k_gc (scope ALL, no ageing)", "bytes": 4096 * (st.numAllocated - freed), "us": float(np.mean(gc_times)) * 1e6,
+                        "GB/s": 4096 * (st.numAllocated - freed) / float(np.mean(gc_times)) / 1e9,
+                        "frac": 4096 * (st.numAllocated - freed) / float(np.mean(gc_times)) / 1e9 / peak, "released": int(freed)},
             "note": "working set > 2x L2 (126 MB), 5 timed launches after 3 warm-ups, no L2 flush needed"}
 
 

@@ -9,6 +9,7 @@ NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum -s 60 -c 120 --csv --log-file gpurun_out/launches_${R}.csv python tools/prof_target.py frame 2 > gpurun_out/launches_${R}.log 2>&1
 # top kernels, full sets
 $NCU --set full --import-source on -k regex:k_integrate -s 1 -c 1 -f -o gpurun_out/prof_integrate_${R} python tools/prof_target.py integrate 3 > gpurun_out/prof_integrate_${R}.log 2>&1
+$NCU --set full --import-source on -k regex:k_gc$ -c 1 -f -o gpurun_out/prof_gc_${R} python tools/prof_target.py integrate 1 > gpurun_out/prof_gc_${R}.log 2>&1
 $NCU --set full --import-source on -k regex:k_icp_iter -s 25 -c 1 -f -o gpurun_out/prof_icp_${R} python tools/prof_target.py icp 1 > gpurun_out/prof_icp_${R}.log 2>&1
 $NCU --set full --import-source on -k regex:k_alloc -s 4 -c 1 -f -o gpurun_out/prof_alloc_${R} python tools/prof_target.py icp 1 > gpurun_out/prof_alloc_${R}.log 2>&1
 $NCU --set full --import-source on -k regex:k_compact -s 4 -c 1 -f -o gpurun_out/prof_compact_${R} python tools/prof_target.py icp 1 > gpurun_out/prof_compact_${R}.log 2>&1

@@ -28,6 +28,7 @@ if what == "integrate":          # large-volume integrate: working set > 2x L2
     ctx.compact()
     for _ in range(reps):
         ctx.integrate_depthf(df)
+    ctx.garbage_collect(1, 0.0, 0.0)     # k_gc over the same 1.46 GB (read-only scan)
     torch.cuda.synchronize()
     st = ctx.stats()
     print("visible", st.numVisible, "updated", st.numUpdated, "alloc", st.numAllocated, "dropped", st.dropped)
