@@ -38,7 +38,9 @@ def owner_of(x: int, y: int, z: int, parts: int) -> int:
 class PartitionedTracker:
     """Per-rank driver of one partition: broadcast -> preprocess -> split ICP + all-reduce -> fuse."""
 
-    def __init__(self, ctx, rank: int, world: int, iterations: int | None = None, group=None):
+    def __init__(self, ctx, rank: int, world: int, iterations: int | None = None, group=None, overlap: bool = True):
+        """overlap: fuse frame k on a second stream beside the broadcast / pre-processing / tracking of frame k+1
+        (frame-to-frame ICP does not read the model); results are identical, the model lags the pose until flush()."""
         import torch
         import torch.distributed as dist
 
@@ -55,6 +57,11 @@ class PartitionedTracker:
         self.frame = 0
         self.launches = 0
         self.fused = False
+        self.overlap = bool(overlap)
+        self._fuse_stream = torch.cuda.Stream() if self.overlap else None
+        self._ev_pose = torch.cuda.Event() if self.overlap else None
+        self._ev_fused = torch.cuda.Event() if self.overlap else None
+        self._fuse_pending = False
         if world > 1:
             self._setup_peer_exchange()
 
@@ -82,7 +89,14 @@ class PartitionedTracker:
             print(f"[rank {self.rank}] symmetric memory unavailable ({e}); ICP all-reduce through NCCL", file=sys.stderr)
             self.fused = False
 
+    def flush(self):
+        """Order the current stream behind the fusion of the latest pushed frame (no-op without overlap)."""
+        if self._fuse_pending:
+            self.torch.cuda.current_stream().wait_event(self._ev_fused)
+            self._fuse_pending = False
+
     def reset(self, pose):
+        self.flush()
         self.d_pose.copy_(self.torch.from_numpy(np.ascontiguousarray(pose, dtype=np.float32).reshape(16)))
         self.ctx.icp_reset(True)
         self.frame = 0
@@ -111,13 +125,27 @@ class PartitionedTracker:
                     dist.all_reduce(self.sys, group=self.group)                           # 32 floats
                     ctx.icp_solve(self.sys)
                     self.launches += 2
+        # the frame constants and per-frame counters change now: the previous frame's fusion must be through
+        self.flush()
+        if self.frame > 0:
             ctx.pose_compose(self.d_pose, self.d_pose)        # T_k = T_{k-1} * delta, also publishes the frame pose
         else:
             ctx.set_pose_device(self.d_pose)
         self.launches += 1
-        ctx.alloc_blocks(v, n)
-        ctx.compact()
-        ctx.integrate_depthf(df)
+        if self.overlap:
+            main = self.torch.cuda.current_stream()
+            self._ev_pose.record(main)
+            fs = self._fuse_stream
+            fs.wait_event(self._ev_pose)
+            ctx.alloc_blocks(v, n, fs)
+            ctx.compact(fs)
+            ctx.integrate_depthf(df, fs)
+            self._ev_fused.record(fs)
+            self._fuse_pending = True
+        else:
+            ctx.alloc_blocks(v, n)
+            ctx.compact()
+            ctx.integrate_depthf(df)
         self.launches += 3
         self.frame += 1
 
