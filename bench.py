@@ -90,31 +90,44 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.idx, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = 0.0
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx), "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.idx), "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi needs 0.1-1 s to start (longer on an 8-GPU box with 8 ranks doing the same): wait for its first
+            # row so that the sampler is already streaming when the timed region begins
+            deadline = time.time() + 5.0
+            while not self.rows and time.time() < deadline:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
+        self.t0 = time.time()
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
+        self.t1 = time.time()
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.06)                     # one more period: the row covering the end of the region
             self.proc.terminate()
             with contextlib.suppress(Exception):
                 self.proc.wait(timeout=2)
 
     def summary(self) -> dict:
+        inside = [r for t, r in self.rows if self.t0 <= t <= self.t1 + 0.06]
+        note = None
+        if not inside and self.rows:             # region shorter than one sampling period: nearest row
+            inside = [min(self.rows, key=lambda tr: abs(tr[0] - self.t1))[1]]
+            note = "timed region shorter than the 50 ms sampling period: nearest sample"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -124,7 +137,10 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def ncu_traffic(kernel_prefix: str):
@@ -450,6 +466,7 @@ def run_multi(args, rank, world, local):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = tracker.launches
     with ClockSampler(local) as cs:
+        dist.barrier()                                   # the samplers start at different speeds: line the ranks up again
         torch.cuda.synchronize()
         ev0.record(stream)
         upd = 0
