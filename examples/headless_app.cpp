@@ -3,9 +3,13 @@
 // Align, getTransform, integrate.  Inputs are two synthetic frames (plane z = 2.5 m + sphere) instead
 // of assets/T0.png / T1.png, which the reference does not ship.
 //   usage: vh_headless_app [dump.txt]
+//          vh_headless_app --frames a.png b.png [...]      16-bit depth PNG / PGM files (TUM convention, 5000 per metre),
+//                                                          read like the reference's stbi_load_16 (Application.cpp:28-29)
+//                                                          and pushed through the native frame pipeline
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -29,7 +33,50 @@ static std::vector<uint16_t> renderFrame(float camX) {
     return d;
 }
 
+// --frames: every file is one frame of a sequence; track frame-to-frame, fuse, print the camera poses.
+static int runSequence(int n, char** files) {
+    vh_config cfg;
+    vh_default_config(&cfg);
+    cfg.policy = VH_POLICY_FIXED;
+    cfg.table.numBuckets = 100003; cfg.table.numVoxelBlocks = 65536; cfg.table.truncation = 0.06f; cfg.icpNormalThres = 0.8f;
+    vh_context* ctx = nullptr;
+    vh_pipeline* pipe = nullptr;
+    uint16_t* d_depth = nullptr;
+    for (int i = 0; i < n; ++i) {
+        uint16_t* img = nullptr;
+        int w = 0, h = 0;
+        if (vh_depth_read(files[i], &img, &w, &h) != VH_OK) { std::fprintf(stderr, "%s: %s\n", files[i], vh_depth_last_error()); return 1; }
+        if (!ctx) {                                       // the first frame fixes the image size (intrinsics scale with it)
+            const float sx = w / 640.0f, sy = h / 480.0f;
+            cfg.width = w; cfg.height = h; cfg.fx *= sx; cfg.cx *= sx; cfg.fy *= sy; cfg.cy *= sy;
+            if (vh_create(&cfg, &ctx) != VH_OK || vh_pipeline_create(ctx, 20, VH_TRACK_FRAME_TO_FRAME, VH_PIPE_GRAPH | VH_PIPE_OVERLAP, &pipe) != VH_OK) {
+                std::fprintf(stderr, "%s\n", vh_last_error());
+                return 1;
+            }
+            vh_pipeline_reset(pipe, nullptr, nullptr);
+            cudaMalloc(&d_depth, sizeof(uint16_t) * w * h);
+        } else if (w != cfg.width || h != cfg.height) {
+            std::fprintf(stderr, "%s: %dx%d, expected %dx%d\n", files[i], w, h, cfg.width, cfg.height);
+            return 1;
+        }
+        cudaMemcpy(d_depth, img, sizeof(uint16_t) * w * h, cudaMemcpyHostToDevice);
+        vh_depth_free(img);
+        if (vh_pipeline_push_device(pipe, d_depth, nullptr) != VH_OK) return 1;
+        float T[16];
+        vh_pipeline_pose(pipe, T, nullptr);
+        std::printf("frame %d  t = (% .5f % .5f % .5f)\n", i, T[3], T[7], T[11]);
+    }
+    vh_stats st;
+    vh_get_stats(ctx, &st, nullptr);
+    std::printf("allocated blocks %d, visible %d, dropped %d\n", st.numAllocated, st.numVisible, st.dropped);
+    vh_pipeline_destroy(pipe);
+    vh_destroy(ctx);
+    cudaFree(d_depth);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 2 && std::string(argv[1]) == "--frames") return runSequence(argc - 2, argv + 2);
     const size_t px = 640 * 480;
     CameraTracking tracker(640, 480);                    // Application.cpp:32
     SDF_Hashtable fusionModule;                          // :33

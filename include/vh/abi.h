@@ -279,6 +279,18 @@ int vh_load(vh_context* ctx, const char* path);
 /* The reference's text dump (SDFRenderer.cpp:71-110) of the compact list. */
 int vh_dump_text(vh_context* ctx, const char* path);
 
+/* ---- depth images on the input side (host only, no device needed) -----------------------------------
+ * The reference reads its frames with stbi_load_16("assets/T0.png", ...) (Application.cpp:28-29, vendored
+ * stb_image.h): raw uint16 samples, 5000 per metre.  vh_depth_read decodes that format without third-party code
+ * beyond zlib -- PNG (grey / colour, 8 / 16 bit, non-interlaced, CRC-checked; stb's conventions: 8-bit samples are
+ * widened as v * 257, the first channel of a multi-channel file is returned) or binary PGM (P5) -- into a malloc'ed
+ * row-major buffer the caller releases with vh_depth_free.  vh_depth_write_png writes 16-bit grey PNGs with the
+ * given scanline filter (0..4). */
+int  vh_depth_read(const char* path, uint16_t** out, int* width, int* height);
+void vh_depth_free(uint16_t* data);
+int  vh_depth_write_png(const char* path, const uint16_t* data, int width, int height, int filter);
+const char* vh_depth_last_error(void);
+
 /* ---- native frame pipeline (the host loop of Application.cpp:73-84 without host syncs) -------
  * preprocess -> ICP x iterations -> pose <- pose * delta -> alloc -> compact -> integrate
  * [-> raycast], stream-ordered, the tracked part replayed from a CUDA graph. */

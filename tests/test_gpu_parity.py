@@ -831,3 +831,31 @@ def test_stream_out_in_matches_oracle(built_library, oracle, pinned):
     assert ctx.stream_in(ent2, vox2) == 10
     ex, _ = compare_blocks(ctx.block_dict(), all_before)
     assert ex
+
+
+def test_headless_app_tracks_a_png_sequence(built_library, tmp_path):
+    """The C++ host loop on the reference's input format: 16-bit depth PNGs -> vh_depth_read -> native pipeline."""
+    import subprocess
+
+    from voxelhashing_demo_b200 import read_depth, write_depth_png
+    from voxelhashing_demo_b200._build import HOST_DEMO
+
+    cfg = fixed_cfg()
+    poses = [scenes.trajectory_C2(4 * k) for k in range(6)]
+    files = []
+    for k, p in enumerate(poses):
+        d = render(cfg, scenes.scene_S1T(), p)
+        f = tmp_path / f"T{k}.png"
+        write_depth_png(f, d, filter_type=k % 5)
+        assert np.array_equal(read_depth(f), d)
+        files.append(str(f))
+    r = subprocess.run([str(HOST_DEMO), "--frames", *files], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("frame ")]
+    assert len(lines) == 6
+    t_last = np.array([float(x) for x in lines[-1].split("(")[1].rstrip(")").split()])
+    assert np.max(np.abs(t_last - poses[-1][:3, 3])) < 5e-3          # 20 mm of travel tracked to a few mm
+    assert "dropped 0" in r.stdout
+    # and the reference's own two-frame loop (Application.cpp:24-103) still ends in OK
+    r = subprocess.run([str(HOST_DEMO), str(tmp_path / "SDF_dump.txt")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr

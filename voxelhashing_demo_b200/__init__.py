@@ -7,7 +7,7 @@ the reference's host classes (`fusion`), synthetic scenes (`scenes`) and the mul
 raises if the library has not been built -- there is no CPU or PyTorch fallback.
 """
 from .lib import POLICY_FIXED, POLICY_REF_EXACT, VHError, load_library  # noqa: F401
-from .fusion import CameraTracking, Config, Context, FramePipeline, SDF_Hashtable  # noqa: F401
+from .fusion import CameraTracking, Config, Context, FramePipeline, SDF_Hashtable, read_depth, write_depth_png  # noqa: F401
 
-__all__ = ["Config", "Context", "SDF_Hashtable", "CameraTracking", "FramePipeline", "VHError", "load_library",
+__all__ = ["Config", "Context", "SDF_Hashtable", "CameraTracking", "FramePipeline", "VHError", "load_library", "read_depth", "write_depth_png",
            "POLICY_FIXED", "POLICY_REF_EXACT"]

@@ -77,7 +77,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     newest = max(o.stat().st_mtime for o in objs)
     if force or not LIB.exists() or LIB.stat().st_mtime < newest:
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOSTCXX,
-               "-o", str(LIB), *map(str, objs), "-lcudart_static", "-lrt", "-ldl", "-lpthread"]
+               "-o", str(LIB), *map(str, objs), "-lcudart_static", "-lrt", "-ldl", "-lpthread", "-lz"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -41,6 +41,27 @@ def _stream(stream=None) -> int:
     return stream.cuda_stream
 
 
+def read_depth(path) -> np.ndarray:
+    """16-bit depth image (PNG as the reference loads it with stbi_load_16, Application.cpp:28-29, or binary PGM)
+    -> uint16 array [H, W].  Host only."""
+    lib = L.load_library()
+    p = C.POINTER(C.c_uint16)()
+    w, h = C.c_int(), C.c_int()
+    if lib.vh_depth_read(str(path).encode(), C.byref(p), C.byref(w), C.byref(h)) != L.VH_OK:
+        raise L.VHError(f"vh_depth_read({path}): {lib.vh_depth_last_error().decode()}")
+    try:
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value)).copy()
+    finally:
+        lib.vh_depth_free(p)
+
+
+def write_depth_png(path, depth_u16: np.ndarray, filter_type: int = 4) -> None:
+    a = np.ascontiguousarray(depth_u16, dtype=np.uint16)
+    lib = L.load_library()
+    if lib.vh_depth_write_png(str(path).encode(), a.ctypes.data, a.shape[1], a.shape[0], int(filter_type)) != L.VH_OK:
+        raise L.VHError(f"vh_depth_write_png({path}): {lib.vh_depth_last_error().decode()}")
+
+
 @dataclass
 class Config:
     """vh_config with the reference's defaults (common.h:7-50)."""
