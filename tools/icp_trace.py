@@ -18,7 +18,7 @@ import bench  # noqa: E402
 from voxelhashing_demo_b200 import Context  # noqa: E402
 from voxelhashing_demo_b200 import lib as L  # noqa: E402
 
-cfg, scene, traj, _ = bench.workload_config("C2")
+cfg, scene, traj, _ = bench.workload_config("C3" if "c3" in sys.argv else "C2")
 ctx = Context(cfg)
 frames, poses = bench.render_frames(cfg, scene, traj, 2)
 d = torch.from_numpy(frames).cuda()

@@ -113,14 +113,18 @@ __device__ __forceinline__ Corr associate(const View& v, const float* __restrict
 
 // 29 running sums: 21 upper-triangle JtJ (row by row), 6 Jtr, residual sum, count.
 // Unknown order (v, omega) as in the live reference path (Solver.cu:29-34, SE3.cpp:6-9).
+// Each term is ONE fused multiply-add (the file is compiled -fmad=false, so a plain `+= a * b` would be FMUL + FADD:
+// 54 instructions per pixel in an issue-bound loop).  The sums have no bit-exact counterpart in the reference
+// (cuBLAS Sgemv / Ssyrk, Solver.cpp:80-87, whose own accumulation order is unspecified); they are checked against
+// fp64 sums to 1e-5, and the single rounding is the more accurate of the two.
 __device__ __forceinline__ void accumulate(float* acc, const float* J, float r) {
     int k = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = i; j < 6; ++j) acc[k++] += J[i] * J[j];
+        for (int j = i; j < 6; ++j) { acc[k] = fmaf(J[i], J[j], acc[k]); ++k; }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) acc[21 + i] += J[i] * r;
+    for (int i = 0; i < 6; ++i) acc[21 + i] = fmaf(J[i], r, acc[21 + i]);
     acc[27] += r;
     acc[28] += 1.0f;
 }
