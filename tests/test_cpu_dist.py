@@ -128,3 +128,62 @@ def test_two_ranks_equal_one(tmp_path, oracle):
     assert not keys[0] & keys[1]
     whole = {tuple(int(c) for c in e[:3]) for e in table.entries()}
     assert (keys[0] | keys[1]) == whole and min(len(keys[0]), len(keys[1])) > 0.3 * len(whole)
+
+
+def _stream_worker(rank, world, port, out_dir):
+    """Re-partitioning through the streaming calls: every rank streams its far blocks out, the records are
+    all-gathered, and every rank streams in the whole pile -- the ownership test inside stream-in keeps only its own."""
+    import torch.distributed as dist
+
+    from conftest import render, small_cfg
+    from oracle import binding as ob
+    from voxelhashing_demo_b200 import scenes
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        base = dict(policy=POLICY_FIXED, numBuckets=1009, numVoxelBlocks=4096, truncation=0.06, overflowSlots=1024)
+        cfg = small_cfg(partCount=world, partRank=rank, **base)
+        t = ob.OracleTable(cfg)
+        pose = np.eye(4, dtype=np.float32)
+        v, _, df = t.preprocess(render(cfg, scenes.scene_S1(), pose))
+        t.fuse_frame(pose, v, df)
+        before = t.block_dict()
+        ent, vox = t.stream_out((0.0, 0.0, 0.0), 2.2, 4096)
+        # exchange: padded to a common length so a plain all_gather of tensors does it
+        n = torch.tensor([len(ent)])
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n)
+        cap = int(max(c.item() for c in counts))
+        pe = torch.zeros((cap, 5), dtype=torch.int32)
+        pv = torch.zeros((cap, 512, 2), dtype=torch.float32)
+        pe[: len(ent)] = torch.from_numpy(ent)
+        pv[: len(ent)] = torch.from_numpy(vox)
+        ge = [torch.zeros_like(pe) for _ in range(world)]
+        gv = [torch.zeros_like(pv) for _ in range(world)]
+        dist.all_gather(ge, pe)
+        dist.all_gather(gv, pv)
+        accepted = 0
+        for r in range(world):
+            k = int(counts[r].item())
+            accepted += t.stream_in(ge[r][:k].numpy(), gv[r][:k].numpy())
+        after = t.block_dict()
+        same = set(after) == set(before) and all(np.array_equal(after[key], before[key]) for key in after)
+        np.savez(Path(out_dir) / f"s{rank}.npz", moved=len(ent), accepted=accepted, same=int(same), nblocks=len(after),
+                 offered=int(sum(c.item() for c in counts)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_streaming_respects_the_partition(tmp_path, oracle):
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_stream_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ranks = [np.load(tmp_path / f"s{r}.npz") for r in range(2)]
+    for r in ranks:
+        # offered everyone's records, each rank takes back exactly what it streamed out and ends where it started
+        assert int(r["moved"]) > 0 and int(r["offered"]) > int(r["moved"])
+        assert int(r["accepted"]) == int(r["moved"]) and int(r["same"]) == 1
