@@ -470,10 +470,12 @@ def run_multi(args, rank, world, local):
         torch.cuda.synchronize()
         ev0.record(stream)
         upd = 0
+        t_host0 = time.perf_counter()
         for i in range(W, W + K):
             tracker.push(d_frames[order[i]] if rank == 0 else None)
         tracker.flush()                                  # the last frame's fusion belongs to the timed region
         ev1.record(stream)
+        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
         torch.cuda.synchronize()
     dist.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
@@ -491,14 +493,15 @@ def run_multi(args, rank, world, local):
     ev0.record(stream)
     for i in range(W, W + K):
         tracker.push(h_frames[order[i]] if rank == 0 else None)
-        h_pose[i - W].copy_(tracker.d_pose, non_blocking=True)
+        tracker.pose_async(h_pose[i - W])
     tracker.flush()
     ev1.record(stream)
     torch.cuda.synchronize()
     ms_e2e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     # integration alone on this rank's partition (the stage that shards): max over ranks of the device time
-    df = tracker.maps[(tracker.frame - 1) & 1][2]
+    tracker.flush()
+    df = tracker.last_depthf()
     t_int = []
     for i in range(6):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -529,7 +532,8 @@ def run_multi(args, rank, world, local):
             "integrate_stage": {"us_max_over_ranks": float(t_int.item()) * 1e3, "voxels_updated_all_ranks": int(upd.item()),
                                 "voxel_updates_per_s": float(upd.item()) / (float(t_int.item()) * 1e-3),
                                 "note": "k_integrate alone on each rank's partition of the hash space; the stage that shards"},
-            "gpu_launches": int(tracker.launches - l0), "clocks": cs.summary(),
+            "gpu_launches": int(tracker.launches - l0),
+            "host_enqueue_ms_per_step": host_enqueue_ms / K, "clocks": cs.summary(),
             "single_gpu_same_workload": single,
             "e2e": {"value": K / (float(ms_e2e.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(cfg.width * cfg.height * 2),
                     "d2h_bytes_per_step": 64 * world, "ms_per_step": float(ms_e2e.item()) / K},

@@ -320,6 +320,8 @@ int  vh_pipeline_push_device(vh_pipeline* p, const uint16_t* d_depth, vh_stream 
 int  vh_pipeline_push_host(vh_pipeline* p, const uint16_t* h_depth, float* h_pose_out, vh_stream s);
 int  vh_pipeline_pose(vh_pipeline* p, float* pose_rowmajor_host, vh_stream s);   /* synchronises */
 const float* vh_pipeline_pose_device(vh_pipeline* p);
+int  vh_pipeline_pose_async(vh_pipeline* p, float* h_pose_rowmajor_pinned, vh_stream s);   /* stream-ordered D2H, no sync */
+int  vh_pipeline_depthf(vh_pipeline* p, float** d_depthf);   /* dense metric depth of the latest frame */
 /* which = 0: maps of the latest frame; 1: the ICP target the next frame will use. */
 int  vh_pipeline_maps(vh_pipeline* p, int which, float4** d_verts, float4** d_normals);
 long long vh_pipeline_launches(vh_pipeline* p);   /* kernels launched so far */

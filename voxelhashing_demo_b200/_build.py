@@ -41,7 +41,9 @@ def _sources() -> list[Path]:
 
 def _stamp(src: Path) -> str:
     h = hashlib.sha256()
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # flags with the checkout path factored out: the snapshot on the GPU box lives under another root, and an
+    # identical tree must not look stale there
+    h.update(" ".join(NVCC_FLAGS).replace(str(ROOT), "<root>").encode())
     h.update(src.read_bytes())
     for hdr in sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").rglob("*.h")):
         h.update(hdr.read_bytes())
@@ -66,28 +68,51 @@ def _compile(src: Path, verbose: bool) -> Path:
     return obj
 
 
+def _link_if_stale(out: Path, stamp_file: Path, want: str, cmd: list[str], what: str, force: bool) -> None:
+    """Link decisions go by CONTENT stamps, never by mtimes: the gpurun snapshot does not preserve file times, and a
+    box that re-linked because 'the objects look newer' did so from all ranks at once."""
+    if not force and out.exists() and stamp_file.exists() and stamp_file.read_text() == want:
+        return
+    tmp = out.with_name(out.name + f".tmp{os.getpid()}")
+    r = subprocess.run([c if c != str(out) else str(tmp) for c in cmd], capture_output=True, text=True)
+    if r.returncode != 0:
+        tmp.unlink(missing_ok=True)
+        raise RuntimeError(f"{what} failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, out)                         # atomic: a concurrent reader sees the old or the new file, never half of one
+    stamp_file.write_text(want)
+
+
 def build(verbose: bool = False, force: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a and link libvh_b200.so in-tree."""
+    """Compile every CUDA source for sm_100a and link libvh_b200.so in-tree.  Safe to call from several processes at
+    once (one rank per GPU does): the whole step runs under an exclusive file lock and is a no-op when the stamps match."""
+    import fcntl
+
+    PKG.mkdir(exist_ok=True)
+    with open(PKG / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(verbose, force)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool, force: bool) -> Path:
     if force and OBJ.exists():
         shutil.rmtree(OBJ)
     OBJ.mkdir(exist_ok=True)
     srcs = _sources()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
-    newest = max(o.stat().st_mtime for o in objs)
-    if force or not LIB.exists() or LIB.stat().st_mtime < newest:
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOSTCXX,
-               "-o", str(LIB), *map(str, objs), "-lcudart_static", "-lrt", "-ldl", "-lpthread", "-lz"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    lib_want = hashlib.sha256("".join((OBJ / (s.stem + ".stamp")).read_text() for s in srcs).encode()).hexdigest()
+    _link_if_stale(LIB, OBJ / "libvh_b200.stamp", lib_want,
+                   [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOSTCXX,
+                    "-o", str(LIB), *map(str, objs), "-lcudart_static", "-lrt", "-ldl", "-lpthread", "-lz"], "link", force)
     demo_src = ROOT / "examples" / "headless_app.cpp"
-    if demo_src.exists() and (force or not HOST_DEMO.exists() or HOST_DEMO.stat().st_mtime < max(LIB.stat().st_mtime, demo_src.stat().st_mtime)):
-        cmd = [NVCC, "-std=c++17", "-O2", "-ccbin", HOSTCXX, "-I", str(ROOT / "include"), str(demo_src), "-o", str(HOST_DEMO),
-               "-L", str(PKG), "-lvh_b200", "-Xlinker", f"-rpath={PKG}", "-Xlinker", "-rpath=$ORIGIN"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"headless_app build failed:\n{r.stdout}\n{r.stderr}")
+    if demo_src.exists():
+        demo_want = hashlib.sha256((lib_want + hashlib.sha256(demo_src.read_bytes()).hexdigest()).encode()).hexdigest()
+        _link_if_stale(HOST_DEMO, OBJ / "vh_headless_app.stamp", demo_want,
+                       [NVCC, "-std=c++17", "-O2", "-ccbin", HOSTCXX, "-I", str(ROOT / "include"), str(demo_src), "-o", str(HOST_DEMO),
+                        "-L", str(PKG), "-lvh_b200", "-Xlinker", f"-rpath={PKG}", "-Xlinker", "-rpath=$ORIGIN"], "headless_app build", force)
     return LIB
 
 

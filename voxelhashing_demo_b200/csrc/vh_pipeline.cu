@@ -59,8 +59,14 @@ cudaError_t enqueueIcp(vh_pipeline* p, int par, cudaStream_t s, int* n) {
     vh_context* c = p->ctx;
     const float4* tg = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelVerts : p->verts[1 - par];
     const float4* tgN = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelNormals : p->normals[1 - par];
+    // Partitioned context with peer mailboxes (vh_set_peers): this rank reduces its share of the image rows and the
+    // 32-float all-reduce over NVLink runs inside the kernel's epilogue -- every rank must push the same frames.
+    const int world = c->peers.world > 1 ? c->peers.world : 1, rank = world > 1 ? c->peers.rank : 0;
+    const int base = c->v.H / world, rem = c->v.H % world;
+    const int row0 = rank * base + (rank < rem ? rank : rem), row1 = row0 + base + (rank < rem ? 1 : 0);
     for (int it = 0; it < p->iterations; ++it) {                           // CameraTracking.cpp:35
-        cudaError_t e = launch_icp_iter_ex(c, p->verts[par], p->normals[par], tg, tgN, 0, c->v.H, nullptr, true, it == 0, it > 0, s);
+        cudaError_t e = world > 1 ? launch_icp_iter_peer(c, p->verts[par], p->normals[par], tg, tgN, row0, row1, it == 0, s)
+                                  : launch_icp_iter_ex(c, p->verts[par], p->normals[par], tg, tgN, 0, c->v.H, nullptr, true, it == 0, it > 0, s);
         if (e != cudaSuccess) return e;
     }
     *n = p->iterations;
@@ -87,15 +93,9 @@ cudaError_t enqueueBody(vh_pipeline* p, int par, bool track, cudaStream_t s, int
     cudaError_t e;
     int k = 0;
     const float4* in = p->verts[par];
-    const float4* inN = p->normals[par];
     if (track) {
-        const float4* tg = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelVerts : p->verts[1 - par];
-        const float4* tgN = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelNormals : p->normals[1 - par];
-        for (int it = 0; it < p->iterations; ++it) {                       // CameraTracking.cpp:35
-            e = launch_icp_iter_ex(c, in, inN, tg, tgN, 0, c->v.H, nullptr, true, it == 0, it > 0, s);
-            if (e != cudaSuccess) return e;
-            ++k;
-        }
+        e = enqueueIcp(p, par, s, &k);
+        if (e != cudaSuccess) return e;
         e = launch_set_frame_device(c, p->d_pose, c->icp->delta, p->d_pose, s);   // T_k = T_{k-1} * delta
     } else {
         e = launch_set_frame_device(c, p->d_pose, nullptr, nullptr, s);
@@ -299,6 +299,20 @@ int vh_pipeline_pose(vh_pipeline* p, float* pose16, vh_stream s) {
 }
 
 const float* vh_pipeline_pose_device(vh_pipeline* p) { return p ? p->d_pose : nullptr; }
+
+// Stream-ordered D2H of the latest pose into (pinned) host memory: no synchronisation, no flush of the fusion stream.
+int vh_pipeline_pose_async(vh_pipeline* p, float* h_pose16, vh_stream s) {
+    if (!p || !h_pose16) return pfail(VH_ERR_INVALID, "vh_pipeline_pose_async: null argument");
+    PCUDA(cudaMemcpyAsync(h_pose16, p->d_pose, 16 * sizeof(float), cudaMemcpyDeviceToHost, reinterpret_cast<cudaStream_t>(s)));
+    return VH_OK;
+}
+
+// Dense metric depth (W x H floats) of the latest pushed frame, as the Fixed integration reads it.
+int vh_pipeline_depthf(vh_pipeline* p, float** d_depthf) {
+    if (!p || !d_depthf || p->frame == 0) return pfail(VH_ERR_INVALID, "vh_pipeline_depthf: bad argument / no frame yet");
+    *d_depthf = p->depthf[(int)((p->frame - 1) & 1)];
+    return VH_OK;
+}
 
 // which: 0 = maps of the latest pushed frame, 1 = ICP target of the NEXT frame's tracking
 int vh_pipeline_maps(vh_pipeline* p, int which, float4** verts, float4** normals) {

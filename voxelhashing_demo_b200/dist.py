@@ -64,6 +64,16 @@ class PartitionedTracker:
         self._fuse_pending = False
         if world > 1:
             self._setup_peer_exchange()
+        # With the exchange fused into the ICP kernel the whole frame is stream-ordered device work, so it goes through
+        # the native frame pipeline (CUDA graphs; the host enqueues ~5 calls per frame instead of ~30 -- the Python
+        # loop below needed 0.4 ms of host time per frame and capped the 4- and 8-GPU runs).  The NCCL-per-iteration
+        # fallback cannot be captured that way and keeps the Python loop.
+        self.pipe = None
+        if self.fused or world == 1:
+            from .fusion import FramePipeline
+
+            self.pipe = FramePipeline(ctx, iterations=self.iterations, mode=FramePipeline.FRAME_TO_FRAME, use_graph=True,
+                                      overlap=self.overlap)
 
     def _setup_peer_exchange(self):
         """Symmetric (peer-mapped) exchange regions so the 32-float all-reduce runs INSIDE the ICP kernel's
@@ -91,12 +101,19 @@ class PartitionedTracker:
 
     def flush(self):
         """Order the current stream behind the fusion of the latest pushed frame (no-op without overlap)."""
+        if self.pipe is not None:
+            self.pipe.flush()
+            return
         if self._fuse_pending:
             self.torch.cuda.current_stream().wait_event(self._ev_fused)
             self._fuse_pending = False
 
     def reset(self, pose):
         self.flush()
+        if self.pipe is not None:
+            self.pipe.reset(np.ascontiguousarray(pose, dtype=np.float32))
+            self.frame = 0
+            return
         self.d_pose.copy_(self.torch.from_numpy(np.ascontiguousarray(pose, dtype=np.float32).reshape(16)))
         self.ctx.icp_reset(True)
         self.frame = 0
@@ -109,6 +126,12 @@ class PartitionedTracker:
             self.depth.copy_(d_depth.view(self.depth.dtype), non_blocking=True)    # device or pinned host source
         if self.world > 1:
             dist.broadcast(self.depth.view(self.torch.uint8), src=0, group=self.group)   # raw bytes over NVLink / NVSwitch
+        if self.pipe is not None:
+            l0 = self.pipe.launches()
+            self.pipe.push_device(self.depth)
+            self.launches += self.pipe.launches() - l0
+            self.frame += 1
+            return
         par = self.frame & 1
         v, n, df = self.maps[par]
         pv, pn, _ = self.maps[1 - par]
@@ -150,5 +173,22 @@ class PartitionedTracker:
         self.frame += 1
 
     def pose(self) -> np.ndarray:
+        if self.pipe is not None:
+            p = self.pipe.pose()
+            self.torch.cuda.synchronize()
+            return p
         self.torch.cuda.synchronize()
         return self.d_pose.cpu().numpy().reshape(4, 4)
+
+    def pose_async(self, h_pose_pinned):
+        """Stream-ordered D2H of the current pose into a pinned host tensor of 16 floats (the e2e read-back)."""
+        if self.pipe is not None:
+            self.pipe.pose_async(h_pose_pinned)
+        else:
+            h_pose_pinned.copy_(self.d_pose, non_blocking=True)
+
+    def last_depthf(self):
+        """Dense metric depth of the latest frame: device address (native pipeline) or tensor (Python loop)."""
+        if self.pipe is not None:
+            return self.pipe.depthf_ptr()
+        return self.maps[(self.frame - 1) & 1][2]

@@ -416,5 +416,15 @@ class FramePipeline:
         L.check(self.lib.vh_pipeline_pose(self._p, out.ctypes.data, _stream(stream)), "vh_pipeline_pose")
         return out.reshape(4, 4)
 
+    def pose_async(self, h_pose_pinned, stream=None):
+        """Stream-ordered copy of the latest pose into a pinned host tensor (16 floats); no synchronisation."""
+        L.check(self.lib.vh_pipeline_pose_async(self._p, _ptr(h_pose_pinned), _stream(stream)), "vh_pipeline_pose_async")
+
+    def depthf_ptr(self) -> int:
+        """Device address of the dense metric depth (W x H floats) of the latest pushed frame."""
+        p = C.c_void_p()
+        L.check(self.lib.vh_pipeline_depthf(self._p, C.byref(p)), "vh_pipeline_depthf")
+        return int(p.value)
+
     def launches(self) -> int:
         return int(self.lib.vh_pipeline_launches(self._p))

@@ -107,7 +107,7 @@ HANDLE_SYMBOLS = [
     "vh_compact_table_device", "vh_compact_counter_device", "vh_voxel_blocks_device", "vh_save", "vh_load",
     "vh_dump_text", "vh_depth_read", "vh_depth_free", "vh_depth_write_png", "vh_depth_last_error",
     "vh_pipeline_create", "vh_pipeline_flush", "vh_pipeline_destroy", "vh_pipeline_reset", "vh_pipeline_push_device",
-    "vh_pipeline_push_host", "vh_pipeline_pose", "vh_pipeline_pose_device", "vh_pipeline_maps", "vh_pipeline_launches",
+    "vh_pipeline_push_host", "vh_pipeline_pose", "vh_pipeline_pose_device", "vh_pipeline_pose_async", "vh_pipeline_depthf", "vh_pipeline_maps", "vh_pipeline_launches",
 ]
 
 _lib = None
@@ -190,6 +190,8 @@ def load_library() -> C.CDLL:
     lib.vh_pipeline_push_device.argtypes = [P, P, P]
     lib.vh_pipeline_push_host.argtypes = [P, P, P, P]
     lib.vh_pipeline_pose.argtypes = [P, P, P]
+    lib.vh_pipeline_pose_async.argtypes = [P, P, P]
+    lib.vh_pipeline_depthf.argtypes = [P, C.POINTER(P)]
     lib.vh_pipeline_pose_device.argtypes = [P]
     lib.vh_pipeline_pose_device.restype = P
     lib.vh_pipeline_maps.argtypes = [P, I, C.POINTER(P), C.POINTER(P)]
