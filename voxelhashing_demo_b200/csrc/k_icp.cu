@@ -347,22 +347,25 @@ __device__ __noinline__ void solveAndUpdateWarp(const float* sys, IcpState* st, 
 // (t >> 3), (t >> 3) + R, ... (R = blockDim/8; <= 3 independent loads for 148 CTAs x 512 threads), sums
 // them in fp64, and 32 threads add the R row-group sums in order.  Fixed order => deterministic.
 // ---- fused cross-GPU all-reduce (one process per GPU, peer memory over NVLink / NVSwitch) --------------
-__device__ __forceinline__ void stReleaseSys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ unsigned ldAcquireSys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// Warp 0 of the last CTA: scatter this rank's 32 partial sums into every rank's exchange region (P2P stores over
+// NVLink), wait for all ranks' contributions, add them in RANK ORDER (so every rank holds the bit-identical system
+// and solves the identical pose: no second broadcast).
+// Low-latency protocol: every value travels WITH the sequence number of the exchange in one 8-byte store
+// (single-copy atomic), and the receiver polls the word until the sequence matches -- no data/flag pair, hence no
+// MEMBAR.SYS + release store + acquire load on the critical path (the first form cost ~10 us per iteration at 8
+// GPUs: two NVLink round trips; this one costs one one-way trip).
+// Regions are double-buffered on the sequence parity: a rank can run at most one exchange ahead of the slowest
+// rank, because it cannot finish exchange k+1 without that rank's contribution to k+1.
+__device__ __forceinline__ void stPairSys(float* p, float v, unsigned seq) {
+    asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
 }
-__device__ __forceinline__ float ldRelaxedSys(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ float ldPairSys(const float* p, unsigned seq) {
+    unsigned v, s;
+    do {
+        asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(s) : "l"(p) : "memory");
+    } while (s != seq);
+    return __uint_as_float(v);
 }
-// Warp 0 of the last CTA: scatter this rank's 32 partial sums into every rank's exchange region (P2P
-// stores), publish a sequence-numbered flag, wait for all ranks' flags, add the contributions in RANK
-// ORDER (so every rank holds the bit-identical system and solves the identical pose: no second broadcast).
-// Regions are double-buffered on the sequence parity: a rank can run at most one exchange ahead of the
-// slowest rank, because it cannot finish exchange k+1 without that rank's contribution to k+1.
 __device__ void peerAllReduce(const PeerView& pv, Counters* ctr, float* sSys) {
     const int lane = threadIdx.x & 31;
     unsigned seq = 0;
@@ -370,17 +373,9 @@ __device__ void peerAllReduce(const PeerView& pv, Counters* ctr, float* sSys) {
     seq = __shfl_sync(0xffffffffu, seq, 0);
     const unsigned slot = seq & 1u;
     const float mine = sSys[lane];
-    for (int p = 0; p < pv.world; ++p) pv.buf[p][(slot * kMaxPeers + pv.rank) * 32 + lane] = mine;
-    __threadfence_system();
-    __syncwarp();
-    if (lane < pv.world) stReleaseSys(reinterpret_cast<unsigned*>(pv.buf[lane] + kPeerDataFloats) + slot * kMaxPeers + pv.rank, seq);
-    if (lane < pv.world) {
-        const unsigned* f = reinterpret_cast<const unsigned*>(pv.buf[pv.rank] + kPeerDataFloats) + slot * kMaxPeers + lane;
-        while (ldAcquireSys(f) != seq) { }
-    }
-    __syncwarp();
+    for (int p = 0; p < pv.world; ++p) stPairSys(pv.buf[p] + ((slot * kMaxPeers + pv.rank) * 32 + lane) * 2, mine, seq);
     float t = 0.f;
-    for (int r = 0; r < pv.world; ++r) t += ldRelaxedSys(pv.buf[pv.rank] + (slot * kMaxPeers + r) * 32 + lane);
+    for (int r = 0; r < pv.world; ++r) t += ldPairSys(pv.buf[pv.rank] + ((slot * kMaxPeers + r) * 32 + lane) * 2, seq);
     sSys[lane] = t;
     if (lane == 0) ctr->icpSeq = seq;
     __syncwarp();

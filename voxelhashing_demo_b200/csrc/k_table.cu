@@ -22,6 +22,7 @@ __global__ void k_reset(View v) {
         Counters c{};
         c.heapCounter = (int)v.numVoxelBlocks - 1;   // ref :207
         c.heapLow = c.heapCounter;
+        c.icpSeq = v.ctr->icpSeq;                    // the peers' mailboxes still hold the old sequence numbers
         *v.ctr = c;
     }
 }

@@ -149,6 +149,7 @@ int vh_create(const vh_config* cfg, vh_context** out) {
     chk(devAlloc(c, &v.compact16, N));
     chk(devAlloc(c, &v.compact20, N));
     chk(devAlloc(c, &v.ctr, (size_t)1));
+    if (e == cudaSuccess) chk(cudaMemset(v.ctr, 0, sizeof(Counters)));   // k_reset carries icpSeq over: it must start defined
     chk(devAlloc(c, &c->frame, (size_t)1));
     {   // IcpState followed by the fp64 solver state
         void* p = nullptr;

@@ -85,8 +85,8 @@ constexpr int kIcpMaxBlocks = 1024;
 // Fused all-reduce of the ICP normal equations over NVLink peer memory.
 // buf[p] = rank p's exchange region mapped into this process: float data[2][8][32], then unsigned flag[2][8].
 constexpr int kMaxPeers = 8;
-constexpr int kPeerDataFloats = 2 * kMaxPeers * 32;
-constexpr size_t kPeerBytes = (kPeerDataFloats + 2 * kMaxPeers) * 4;
+// exchange region: 2 parity slots x kMaxPeers ranks x 32 values x {float value, u32 sequence}
+constexpr size_t kPeerBytes = 2 * kMaxPeers * 32 * 8;
 struct PeerView { int world, rank; float* buf[kMaxPeers]; };
 
 struct Pose16f { float m[16]; };
