@@ -149,6 +149,9 @@ __device__ void insertRefExact(const View& v, int x, int y, int z) {
 template <class P>
 __device__ __forceinline__ void warpRequest(const View& v, const float* pose, unsigned long long* filter, bool have, int x, int y, int z) {
     const unsigned lane = threadIdx.x & 31;
+    // partitioned hash space: drop what another rank owns BEFORE the warp / CTA de-duplication, so (P-1)/P of the
+    // requests never reach the match, the filter or the table (the scan itself is replicated on every rank)
+    if (P::fixed) have = have && ownedHere(v, x, y, z);
     const unsigned mask = __ballot_sync(0xffffffffu, have);
     if (!have) return;
     const unsigned h32 = blockHash32(x, y, z);
@@ -163,7 +166,6 @@ __device__ __forceinline__ void warpRequest(const View& v, const float* pose, un
         if (old == packed) return;                          // already forwarded by this CTA
     }
     if (P::fixed) {
-        if (!ownedHere(v, x, y, z)) return;
         bool fresh;
         insertFixed(v, x, y, z, fresh);
     } else {

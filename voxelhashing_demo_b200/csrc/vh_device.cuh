@@ -49,7 +49,10 @@ __device__ __forceinline__ unsigned int ownerMix(int x, int y, int z) {
     return u;
 }
 __device__ __forceinline__ bool ownedHere(const View& v, int x, int y, int z) {
-    return v.partCount <= 1 || (int)(ownerMix(x, y, z) % (unsigned)v.partCount) == v.partRank;
+    if (v.partCount <= 1) return true;
+    const unsigned u = ownerMix(x, y, z), P = (unsigned)v.partCount;
+    // the test runs per lane per DDA step of the allocation scan: a mask instead of a division for 2, 4, 8 ranks
+    return (int)((P & (P - 1u)) == 0u ? (u & (P - 1u)) : (u % P)) == v.partRank;
 }
 
 // ---- RefExact coordinate maps (VoxelUtils.cu:266-309) -----------------------------------------
