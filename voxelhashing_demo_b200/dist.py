@@ -49,7 +49,14 @@ class PartitionedTracker:
         self.iterations = iterations or ctx.cfg.icpIterations
         cfg = ctx.cfg
         n = cfg.width * cfg.height
-        self.depth = torch.zeros(n, dtype=torch.uint16, device="cuda") if hasattr(torch, "uint16") else torch.zeros(n, dtype=torch.int16, device="cuda")
+        dt = torch.uint16 if hasattr(torch, "uint16") else torch.int16
+        # two landing buffers: the copy + broadcast of frame k+1 run on their own stream while frame k is being tracked
+        self._depths = [torch.zeros(n, dtype=dt, device="cuda"), torch.zeros(n, dtype=dt, device="cuda")]
+        self.depth = self._depths[0]
+        self._bcast_stream = torch.cuda.Stream()
+        self._ev_arrived = [torch.cuda.Event(), torch.cuda.Event()]
+        self._ev_consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self._pushed = 0
         self.maps = [ctx.new_maps(), ctx.new_maps()]
         self.sys = torch.zeros(32, dtype=torch.float32, device="cuda")
         self.d_pose = torch.zeros(16, dtype=torch.float32, device="cuda")
@@ -118,17 +125,35 @@ class PartitionedTracker:
         self.ctx.icp_reset(True)
         self.frame = 0
 
-    def push(self, d_depth=None):
+    def push(self, d_depth=None, input_ready: bool = False):
         """One frame.  Rank 0 passes the depth image (device tensor, or pinned host tensor for the end-to-end
-        path); the others pass None."""
-        ctx, dist = self.ctx, self.dist
-        if self.rank == 0:
-            self.depth.copy_(d_depth.view(self.depth.dtype), non_blocking=True)    # device or pinned host source
-        if self.world > 1:
-            dist.broadcast(self.depth.view(self.torch.uint8), src=0, group=self.group)   # raw bytes over NVLink / NVSwitch
+        path); the others pass None.  input_ready=True promises that the image is already complete in memory (a
+        resident sequence, a pinned host buffer filled earlier): the copy + broadcast then start right away on their
+        own stream and overlap the tracking of the previous frame.  Otherwise they are ordered behind everything
+        enqueued on the current stream so far, which is always safe."""
+        ctx, dist, torch = self.ctx, self.dist, self.torch
+        main = torch.cuda.current_stream()
+        slot = self._pushed & 1
+        self.depth = self._depths[slot]
+        bs = self._bcast_stream
+        if self._pushed >= 2 and input_ready:
+            bs.wait_event(self._ev_consumed[slot])           # the pre-processing of frame k-2 has read this buffer
+        else:
+            bs.wait_stream(main)                             # behind the producer of d_depth (and all earlier work)
+        with torch.cuda.stream(bs):
+            if self.rank == 0:
+                if d_depth.is_cuda:
+                    d_depth.record_stream(bs)
+                self.depth.copy_(d_depth.view(self.depth.dtype), non_blocking=True)    # device or pinned host source
+            if self.world > 1:
+                dist.broadcast(self.depth.view(torch.uint8), src=0, group=self.group)   # raw bytes over NVLink / NVSwitch
+            self._ev_arrived[slot].record(bs)
+        main.wait_event(self._ev_arrived[slot])
+        self._pushed += 1
         if self.pipe is not None:
             l0 = self.pipe.launches()
             self.pipe.push_device(self.depth)
+            self._ev_consumed[slot].record(main)             # conservative: recorded behind the whole push, not only the pre-processing
             self.launches += self.pipe.launches() - l0
             self.frame += 1
             return
@@ -136,6 +161,7 @@ class PartitionedTracker:
         v, n, df = self.maps[par]
         pv, pn, _ = self.maps[1 - par]
         ctx.preprocess(self.depth, v, n, df)
+        self._ev_consumed[slot].record(main)
         self.launches += 1
         if self.frame > 0:
             if self.fused or self.world == 1:
