@@ -7,6 +7,12 @@
 // The braces are a CUDA graph (one per buffer parity in frame-to-frame mode, where the previous
 // frame's maps are the ICP target).  The pose lives in device memory and is chained on the device,
 // so frame k+1 can be enqueued before frame k has finished.
+//
+// VH_PIPE_OVERLAP (frame-to-frame): two graphs per parity -- { ICP x iterations } on the caller's stream and
+// { alloc -> compact -> integrate } on an internal stream that starts once pose_k is published; the caller's
+// stream goes straight on to frame k+1 and only waits for fusion(k) before pose_{k+1} replaces the frame
+// constants.  On a partitioned context with peer mailboxes (vh_set_peers) the ICP graph reduces this rank's image
+// rows and carries the cross-GPU all-reduce in its kernels' epilogue.
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -202,7 +208,6 @@ static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, c
     p->launches += 1;
     const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
     int n = 0;
-    const int slot = p->mode == VH_TRACK_FRAME_TO_MODEL ? 0 : par;
     if (p->overlap && st != nullptr) {
         // caller's stream:  preprocess(k) -> ICP(k) x iterations -> [wait fusion(k-1)] -> pose_k, frame constants
         // fusion stream:    [wait pose_k] -> alloc(k) -> compact -> integrate(k)
@@ -252,7 +257,6 @@ static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, c
     } else {
         PCUDA(enqueueBody(p, par, track, st, &n));
     }
-    (void)slot;
     p->launches += n;
     p->frame += 1;
     return VH_OK;
