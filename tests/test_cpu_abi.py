@@ -121,3 +121,24 @@ def test_invalid_configs_are_rejected_before_touching_a_device(built_library):
     assert lib.vh_icp_align(null, None, None, None, None, 1, None) == L.VH_ERR_INVALID
     assert lib.vh_raycast(null, None, None, None) == L.VH_ERR_INVALID
     assert lib.vh_set_peers(null, 0, 1, None) == L.VH_ERR_INVALID
+
+
+def test_build_is_safe_from_several_processes_and_ignores_mtimes(built_library, tmp_path):
+    """One rank per GPU calls build() at the same moment on a box whose snapshot does not preserve file times:
+    nothing may be re-linked (content stamps), and concurrent callers must not trip over each other (file lock)."""
+    import os
+    import sys
+    import time
+
+    from voxelhashing_demo_b200 import _build
+
+    before = (_build.LIB.stat().st_ino, _build.LIB.stat().st_size)
+    for o in _build.OBJ.glob("*.o"):                      # make every object look newer than the library
+        os.utime(o, (time.time() + 100, time.time() + 100))
+    code = "import sys; sys.path.insert(0, %r); from voxelhashing_demo_b200 import _build; _build.build()" % str(ROOT)
+    procs = [subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE) for _ in range(4)]
+    for p in procs:
+        out, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err.decode()[-2000:]
+    assert (_build.LIB.stat().st_ino, _build.LIB.stat().st_size) == before, "the library was re-linked although nothing changed"
+    L.load_library()
