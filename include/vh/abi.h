@@ -128,6 +128,11 @@ typedef struct vh_config {
     /* multi-GPU partition of the block-coordinate hash space: this context only inserts
      * blocks with owner(block) == partRank, owner = mix(hash) mod partCount. 1/0 = all. */
     int partCount, partRank;
+    /* Fixed policy, optional (0 = off): 5x5 bilateral filter of the depth image ahead of the vertex / normal maps, as in
+     * the tracking front end of KinectFusion-style pipelines ("a proper bilateral / validity
+     * mask"; the reference has none, CameraTrackingUtils.cu:50-113).  sigma in pixels / metres.  Integration keeps
+     * reading the RAW depth. */
+    float bilateralSigmaSpace, bilateralSigmaRange;
 } vh_config;
 
 typedef struct vh_stats {

@@ -29,6 +29,7 @@ class VoConfig(C.Structure):
         ("integrationWeightSample", C.c_uint), ("integrationWeightMax", C.c_float),
         ("icpDistThres", C.c_float), ("icpNormalThres", C.c_float),
         ("partCount", C.c_int), ("partRank", C.c_int),
+        ("bilateralSigmaSpace", C.c_float), ("bilateralSigmaRange", C.c_float),
     ]
 
 
@@ -146,6 +147,7 @@ def make_config(cfg) -> VoConfig:
     c.integrationWeightSample, c.integrationWeightMax = cfg.integrationWeightSample, cfg.integrationWeightMax
     c.icpDistThres, c.icpNormalThres = cfg.icpDistThres, cfg.icpNormalThres
     c.partCount, c.partRank = max(1, cfg.partCount), cfg.partRank
+    c.bilateralSigmaSpace, c.bilateralSigmaRange = cfg.bilateralSigmaSpace, cfg.bilateralSigmaRange
     return c
 
 

@@ -402,11 +402,48 @@ void vo_preprocess(const vo_config* cfg, const uint16_t* depth, float* verts, fl
     const vo_config& c = *cfg;
     const int W = c.width, H = c.height;
     const bool fixed = c.policy == VO_POLICY_FIXED;
+    // Fixed, optional: 5x5 bilateral filter of the raw depth ahead of the maps (k_preprocess.cu k_bilateral).  The two
+    // weight tables are computed exactly as vh_create computes them; taps in row-major order, sum of weights with
+    // plain adds, weighted sum with one fma per tap.
+    const bool smoothOn = fixed && c.bilateralSigmaSpace > 0.0f && c.bilateralSigmaRange > 0.0f;
+    std::vector<float> smooth;
+    if (smoothOn) {
+        constexpr int kLut = 1024;
+        std::vector<float> lut(kLut);
+        float g[3];
+        const double sr = (double)(c.bilateralSigmaRange * c.depthScale), ss = (double)c.bilateralSigmaSpace;
+        for (int i = 0; i < kLut; ++i) lut[i] = (float)std::exp(-((double)i * (double)i) / (2.0 * sr * sr));
+        for (int i = 0; i < 3; ++i) g[i] = (float)std::exp(-((double)i * (double)i) / (2.0 * ss * ss));
+        smooth.assign((size_t)W * H, 0.0f);
+#pragma omp parallel for schedule(static)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const int d0 = depth[y * W + x];
+                if (d0 == 0) continue;
+                float sumW = 0.0f, sumD = 0.0f;
+                for (int dy = -2; dy <= 2; ++dy) {
+                    const int yy = y + dy;
+                    if (yy < 0 || yy >= H) continue;
+                    for (int dx = -2; dx <= 2; ++dx) {
+                        const int xx = x + dx;
+                        if (xx < 0 || xx >= W) continue;
+                        const int dj = depth[yy * W + xx];
+                        const int diff = std::abs(dj - d0);
+                        if (dj == 0 || diff >= kLut) continue;
+                        const float ws = g[std::abs(dy)] * g[std::abs(dx)];
+                        const float w = ws * lut[diff];
+                        sumW = sumW + w;
+                        sumD = fmaf(w, (float)dj, sumD);
+                    }
+                }
+                smooth[(size_t)y * W + x] = sumD / sumW;
+            }
+    }
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
             int idx = y * W + x;
-            float d = (float)depth[idx] / c.depthScale;                   // :63-64
+            float d = (smoothOn ? smooth[idx] : (float)depth[idx]) / c.depthScale;   // :63-64
             if (fixed && !(d > c.depthMin && d < c.depthMax)) d = 0.0f;   // Fixed: sensor range mask
             V3 ic{(float)x, (float)y, 1.0f};                              // :69
             V3 p = mul3(c.Kinv, ic);                                      // :70  K_inv*imageCoord
@@ -414,7 +451,11 @@ void vo_preprocess(const vo_config* cfg, const uint16_t* depth, float* verts, fl
             verts[idx * 4 + 1] = p.y * d;
             verts[idx * 4 + 2] = p.z * d;
             verts[idx * 4 + 3] = 1.0f;                                    // w = 1 always (Q27)
-            if (depthf) depthf[idx] = p.z * d;
+            if (depthf) {                                                 // integration reads the RAW depth
+                float dr = (float)depth[idx] / c.depthScale;
+                if (fixed && !(dr > c.depthMin && dr < c.depthMax)) dr = 0.0f;
+                depthf[idx] = p.z * dr;
+            }
         }
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < H; ++y)

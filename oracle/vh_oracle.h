@@ -37,6 +37,7 @@ typedef struct vo_config {
     float integrationWeightMax;
     float icpDistThres, icpNormalThres;
     int partCount, partRank;
+    float bilateralSigmaSpace, bilateralSigmaRange;   /* Fixed: 5x5 bilateral filter ahead of the maps; 0 = off */
 } vo_config;
 
 typedef struct vo_table vo_table;

@@ -408,3 +408,41 @@ def test_stream_out_in_roundtrip(oracle):
     w = before[k][:, 1]
     assert np.array_equal(merged[k][:, 1], np.minimum(cfg.integrationWeightMax, w + w))
     assert np.max(np.abs(merged[k][:, 0] - before[k][:, 0])) < 1e-6
+
+
+def test_bilateral_front_end_properties(oracle):
+    """Fixed-policy optional bilateral filter: smooths within a surface, never across a depth edge or a hole,
+    leaves the integration depth raw, and is a bit-exact no-op when switched off."""
+    kw = dict(policy=POLICY_FIXED, depthMax=4.0)
+    off, on = small_cfg(**kw), small_cfg(bilateralSigmaSpace=1.5, bilateralSigmaRange=0.03, **kw)
+    H, W = off.height, off.width
+    rng = np.random.default_rng(11)
+    clean = np.full((H, W), 10000, np.uint16)                 # wall at 2 m ...
+    clean[:, W // 2:] = 14000                                 # ... and a step to 2.8 m: 4000 units apart, far beyond the range kernel
+    noisy = (clean.astype(np.int32) + rng.integers(-25, 26, clean.shape)).astype(np.uint16)     # +-5 mm
+    noisy[20:24, 10:14] = 0                                   # a hole
+    t_off, t_on = oracle.OracleTable(off), oracle.OracleTable(on)
+    v0, n0, d0 = t_off.preprocess(noisy)
+    v1, n1, d1 = t_on.preprocess(noisy)
+    assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32))                 # integration depth stays raw
+    z0, z1 = v0[:, 2].reshape(H, W), v1[:, 2].reshape(H, W)
+    inner = np.s_[4:H - 4, 4:W // 2 - 4]                      # left wall, away from the edge, the border and the hole
+    mask = np.ones((H, W), bool)
+    mask[16:28, 6:18] = False
+    sel = np.zeros((H, W), bool)
+    sel[inner] = True
+    sel &= mask
+    assert np.std(z1[sel]) < 0.45 * np.std(z0[sel])           # noise down by more than half
+    assert abs(np.mean(z1[sel]) - 2.0) < 2e-4
+    # no bleeding across the step: both sides keep their own level right up to the edge
+    assert np.all(np.abs(z1[4:H - 4, W // 2 - 1] - 2.0) < 0.006) and np.all(np.abs(z1[4:H - 4, W // 2] - 2.8) < 0.006)
+    # holes stay holes, and their neighbours are averages of valid pixels only
+    assert np.all(z1[20:24, 10:14] == 0) and np.all(np.abs(z1[19, 9:15] - 2.0) < 0.006)
+    # normals of the flat wall get closer to (0, 0, -1) [cross(dy, dx) convention of the reference]
+    nz0, nz1 = np.abs(n0[:, 2].reshape(H, W)[sel]), np.abs(n1[:, 2].reshape(H, W)[sel])
+    assert np.mean(nz1) > np.mean(nz0) and np.mean(nz1) > 0.999
+    # a constant image passes through unchanged (up to the rounding of sum(w d) / sum(w)); sigma = 0 is the unfiltered path bit for bit
+    flat = np.full((H, W), 9000, np.uint16)
+    assert np.allclose(t_on.preprocess(flat)[0], t_off.preprocess(flat)[0], rtol=3e-7, atol=0)
+    zero_sigma = oracle.OracleTable(small_cfg(bilateralSigmaSpace=0.0, bilateralSigmaRange=0.03, **kw))
+    assert np.array_equal(zero_sigma.preprocess(noisy)[0].view(np.uint32), v0.view(np.uint32))

@@ -859,3 +859,44 @@ def test_headless_app_tracks_a_png_sequence(built_library, tmp_path):
     # and the reference's own two-frame loop (Application.cpp:24-103) still ends in OK
     r = subprocess.run([str(HOST_DEMO), str(tmp_path / "SDF_dump.txt")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+
+
+# ---- optional bilateral front end (SURVEY 8 f1) --------------------------------------------------------
+@pytest.mark.parametrize("size", ["vga", "ragged"])
+def test_bilateral_preprocess_bit_exact(built_library, oracle, size):
+    kw = dict(bilateralSigmaSpace=1.5, bilateralSigmaRange=0.03)
+    cfg = fixed_cfg(**kw) if size == "vga" else fixed_cfg(width=161, height=123, fx=517.3 / 4, fy=516.5 / 4, cx=318.6 / 4, cy=255.3 / 4, **kw)
+    depth = render(cfg, scenes.scene_S1T(), scenes.trajectory_C2(7))
+    rng = np.random.default_rng(3)
+    depth = np.where(depth > 0, (depth.astype(np.int32) + rng.integers(-20, 21, depth.shape)).clip(1, 65535), 0).astype(np.uint16)
+    depth[5:9, 10:40] = 0
+    ov, on, odf = oracle.OracleTable(cfg).preprocess(depth)
+    ctx = Context(cfg)
+    v, n, df = gpu_preprocess(ctx, depth)
+    assert np.array_equal(bits(v.cpu().numpy()), bits(ov))
+    assert np.array_equal(bits(n.cpu().numpy()), bits(on))
+    assert np.array_equal(bits(df.cpu().numpy()), bits(odf))
+    # and it does something: the filtered map differs from the raw one, the integration depth does not
+    raw = Context(fixed_cfg(width=cfg.width, height=cfg.height, fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy))
+    rv, rn, rdf = gpu_preprocess(raw, depth)
+    assert not torch.equal(rv, v) and torch.equal(rdf, df)
+
+
+def test_bilateral_front_end_helps_tracking_under_noise(built_library, oracle):
+    """+-6 mm uniform depth noise on the C2 sequence: frame-to-frame ICP drifts less with the filtered maps."""
+    errs = {}
+    rng = np.random.default_rng(17)
+    poses = [scenes.trajectory_C2(2 * k) for k in range(25)]
+    base = fixed_cfg(numVoxelBlocks=16384, icpNormalThres=0.8)
+    clean = [render(base, scenes.scene_S1T(), p) for p in poses]
+    noisy = [np.where(d > 0, (d.astype(np.int32) + rng.integers(-30, 31, d.shape)).clip(1, 65535), 0).astype(np.uint16) for d in clean]
+    for name, kw in (("raw", {}), ("bilateral", dict(bilateralSigmaSpace=1.5, bilateralSigmaRange=0.03))):
+        ctx = Context(fixed_cfg(numVoxelBlocks=16384, icpNormalThres=0.8, **kw))
+        pipe = FramePipeline(ctx, iterations=10, mode=FramePipeline.FRAME_TO_FRAME, use_graph=True, overlap=True)
+        pipe.reset(poses[0].astype(np.float32))
+        for d in noisy:
+            pipe.push_device(cu(d.reshape(-1)))
+        pose = pipe.pose()
+        errs[name] = float(np.max(np.abs(pose[:3, 3] - poses[-1][:3, 3])))
+        assert ctx.stats().dropped == 0
+    assert errs["bilateral"] < errs["raw"] and errs["bilateral"] < 0.01, errs

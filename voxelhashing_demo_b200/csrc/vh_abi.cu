@@ -109,6 +109,7 @@ void vh_default_config(vh_config* cfg) {
     cfg->overflowSlots = 0;
     cfg->icpDistThres = 0.08f; cfg->icpNormalThres = -1.0f; cfg->icpIterations = 20;
     cfg->partCount = 1; cfg->partRank = 0;
+    cfg->bilateralSigmaSpace = 0.0f; cfg->bilateralSigmaRange = 0.0f;
 }
 
 int vh_device_count(void) {
@@ -151,6 +152,19 @@ int vh_create(const vh_config* cfg, vh_context** out) {
     chk(devAlloc(c, &v.ctr, (size_t)1));
     if (e == cudaSuccess) chk(cudaMemset(v.ctr, 0, sizeof(Counters)));   // k_reset carries icpSeq over: it must start defined
     chk(devAlloc(c, &c->frame, (size_t)1));
+    if (c->cfg.policy == VH_POLICY_FIXED && c->cfg.bilateralSigmaSpace > 0.0f && c->cfg.bilateralSigmaRange > 0.0f) {
+        // Host-computed tables (the oracle computes the same doubles with the same libm): spatial weights for offsets
+        // 0, 1, 2 and the range weight per raw-unit depth difference.
+        float* lut = nullptr;
+        chk(devAlloc(c, &lut, (size_t)kBilatLut));
+        chk(devAlloc(c, &v.depthSmooth, (size_t)v.W * v.H));
+        std::vector<float> h(kBilatLut);
+        const double sr = (double)(c->cfg.bilateralSigmaRange * c->cfg.depthScale), ss = (double)c->cfg.bilateralSigmaSpace;
+        for (int i = 0; i < kBilatLut; ++i) h[i] = (float)std::exp(-((double)i * (double)i) / (2.0 * sr * sr));
+        for (int i = 0; i < 3; ++i) v.bilatG[i] = (float)std::exp(-((double)i * (double)i) / (2.0 * ss * ss));
+        if (e == cudaSuccess) chk(cudaMemcpy(lut, h.data(), sizeof(float) * kBilatLut, cudaMemcpyHostToDevice));
+        v.bilatLut = lut;
+    }
     {   // IcpState followed by the fp64 solver state
         void* p = nullptr;
         cudaError_t r = cudaMalloc(&p, sizeof(IcpState) + 16 * sizeof(double));
@@ -180,6 +194,7 @@ void vh_destroy(vh_context* c) {
     if (!c) return;
     cudaFree(c->v.entries); cudaFree(c->v.chain); cudaFree(c->v.mutex); cudaFree(c->v.heap);
     cudaFree(c->v.blockInfo); cudaFree(c->v.voxels); cudaFree(c->v.compact16); cudaFree(c->v.compact20);
+    cudaFree(const_cast<float*>(c->v.bilatLut)); cudaFree(c->v.depthSmooth);
     cudaFree(c->v.ctr); cudaFree(c->frame); cudaFree(c->icp); cudaFree(c->icpPartials); cudaFree(c->tileMin); cudaFree(c->tileMax);
     delete c;
 }

@@ -78,9 +78,14 @@ struct View {
     float wr, hb, nl, nr, nt, nb, rad;   // Fixed frustum constants (DESIGN.md "visibility")
     int partCount, partRank;
     float icpDistThres, icpNormalThres;
+    // optional bilateral depth filter (Fixed): spatial weights g[|d|], range LUT over |delta depth| in raw units, scratch image
+    float bilatG[3];
+    const float* bilatLut;           // kBilatLut entries, nullptr = filter off
+    float* depthSmooth;              // W x H filtered depth, raw units as float
 };
 
 constexpr int kIcpMaxBlocks = 1024;
+constexpr int kBilatLut = 1024;      // |delta depth| >= this many raw units contributes nothing
 
 // Fused all-reduce of the ICP normal equations over NVLink peer memory.
 // buf[p] = rank p's exchange region mapped into this process: float data[2][8][32], then unsigned flag[2][8].

@@ -92,6 +92,8 @@ class Config:
     icpIterations: int = 20
     partCount: int = 1
     partRank: int = 0
+    bilateralSigmaSpace: float = 0.0      # pixels; Fixed policy, 0 = off
+    bilateralSigmaRange: float = 0.0      # metres
     extra: dict = field(default_factory=dict)
 
     def to_c(self) -> L.VhConfig:
@@ -109,6 +111,7 @@ class Config:
         c.overflowSlots = self.overflowSlots
         c.icpDistThres, c.icpNormalThres, c.icpIterations = self.icpDistThres, self.icpNormalThres, self.icpIterations
         c.partCount, c.partRank = self.partCount, self.partRank
+        c.bilateralSigmaSpace, c.bilateralSigmaRange = self.bilateralSigmaSpace, self.bilateralSigmaRange
         return c
 
     def K(self) -> np.ndarray:

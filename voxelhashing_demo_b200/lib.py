@@ -65,6 +65,8 @@ class VhConfig(C.Structure):
         ("icpIterations", C.c_int),
         ("partCount", C.c_int),
         ("partRank", C.c_int),
+        ("bilateralSigmaSpace", C.c_float),
+        ("bilateralSigmaRange", C.c_float),
     ]
 
 
