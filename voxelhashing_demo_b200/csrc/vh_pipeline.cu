@@ -205,7 +205,7 @@ static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, c
     const int par = (int)(p->frame & 1);
     PCUDA(launch_preprocess(c, d_depth, p->verts[par], p->normals[par], p->depthf[par], st));   // Application.cpp:73
     if (afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, st));      // the raw depth buffer may be overwritten from here on
-    p->launches += 1;
+    p->launches += (c->v.bilatLut != nullptr && c->cfg.policy == VH_POLICY_FIXED) ? 2 : 1;   // [k_bilateral +] k_preprocess
     const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
     int n = 0;
     if (p->overlap && st != nullptr) {
