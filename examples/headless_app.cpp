@@ -3,7 +3,8 @@
 // Align, getTransform, integrate.  Inputs are two synthetic frames (plane z = 2.5 m + sphere) instead
 // of assets/T0.png / T1.png, which the reference does not ship.
 //   usage: vh_headless_app [dump.txt]
-//          vh_headless_app --frames a.png b.png [...]      16-bit depth PNG / PGM files (TUM convention, 5000 per metre),
+//          vh_headless_app --frames a.png b.png [...] [--mesh out.ply]
+//                                                          16-bit depth PNG / PGM files (TUM convention, 5000 per metre),
 //                                                          read like the reference's stbi_load_16 (Application.cpp:28-29)
 //                                                          and pushed through the native frame pipeline
 #include <cmath>
@@ -34,7 +35,7 @@ static std::vector<uint16_t> renderFrame(float camX) {
 }
 
 // --frames: every file is one frame of a sequence; track frame-to-frame, fuse, print the camera poses.
-static int runSequence(int n, char** files) {
+static int runSequence(int n, char** files, const char* meshPath) {
     vh_config cfg;
     vh_default_config(&cfg);
     cfg.policy = VH_POLICY_FIXED;
@@ -69,6 +70,19 @@ static int runSequence(int n, char** files) {
     vh_stats st;
     vh_get_stats(ctx, &st, nullptr);
     std::printf("allocated blocks %d, visible %d, dropped %d\n", st.numAllocated, st.numVisible, st.dropped);
+    if (meshPath) {                                       // zero level set of the fused model as a binary PLY
+        int nt = 0;
+        vh_pipeline_flush(pipe, nullptr);
+        vh_extract_mesh(ctx, nullptr, 0, &nt, nullptr);
+        float* d_tris = nullptr;
+        std::vector<float> h((size_t)nt * 9);
+        cudaMalloc(&d_tris, sizeof(float) * 9 * (nt > 0 ? nt : 1));
+        vh_extract_mesh(ctx, d_tris, nt, &nt, nullptr);
+        cudaMemcpy(h.data(), d_tris, sizeof(float) * 9 * nt, cudaMemcpyDeviceToHost);
+        cudaFree(d_tris);
+        if (vh_save_mesh_ply(meshPath, h.data(), nt) != VH_OK) return 1;
+        std::printf("mesh: %d triangles -> %s\n", nt, meshPath);
+    }
     vh_pipeline_destroy(pipe);
     vh_destroy(ctx);
     cudaFree(d_depth);
@@ -76,7 +90,12 @@ static int runSequence(int n, char** files) {
 }
 
 int main(int argc, char** argv) {
-    if (argc > 2 && std::string(argv[1]) == "--frames") return runSequence(argc - 2, argv + 2);
+    if (argc > 2 && std::string(argv[1]) == "--frames") {
+        const char* mesh = nullptr;
+        int n = argc - 2;
+        if (n > 2 && std::string(argv[argc - 2]) == "--mesh") { mesh = argv[argc - 1]; n -= 2; }
+        return runSequence(n, argv + 2, mesh);
+    }
     const size_t px = 640 * 480;
     CameraTracking tracker(640, 480);                    // Application.cpp:32
     SDF_Hashtable fusionModule;                          // :33

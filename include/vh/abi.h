@@ -284,6 +284,15 @@ int vh_load(vh_context* ctx, const char* path);
 /* The reference's text dump (SDFRenderer.cpp:71-110) of the compact list. */
 int vh_dump_text(vh_context* ctx, const char* path);
 
+/* Triangle mesh of the zero level set (the reference has no extraction, only the text dump
+ * above).  Marching tetrahedra on the Kuhn subdivision of every voxel cell whose eight corners have been observed;
+ * d_triangles receives 9 floats per triangle (three world-space vertices in metres, normal towards free space).  At
+ * most `capacity` triangles are written; *h_count receives the number the model HAS (call again with a larger
+ * buffer if it exceeds capacity; capacity 0 with d_triangles NULL just counts).  Synchronises.  vh_save_mesh_ply writes
+ * a binary little-endian PLY (vertices not shared) from a HOST copy of such a buffer. */
+int vh_extract_mesh(vh_context* ctx, float* d_triangles, int capacity, int* h_count, vh_stream s);
+int vh_save_mesh_ply(const char* path, const float* h_triangles, int count);
+
 /* ---- depth images on the input side (host only, no device needed) -----------------------------------
  * The reference reads its frames with stbi_load_16("assets/T0.png", ...) (Application.cpp:28-29, vendored
  * stb_image.h): raw uint16 samples, 5000 per metre.  vh_depth_read decodes that format without third-party code

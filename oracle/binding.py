@@ -77,6 +77,8 @@ def oracle_lib() -> C.CDLL:
     lib.vo_compact.restype = I
     lib.vo_garbage_collect.argtypes = [P, I, C.c_float, C.c_float]
     lib.vo_garbage_collect.restype = I
+    lib.vo_extract_mesh.argtypes = [P, P, I]
+    lib.vo_extract_mesh.restype = I
     lib.vo_stream_out.argtypes = [P, P, C.c_float, P, P, I]
     lib.vo_stream_out.restype = I
     lib.vo_stream_in.argtypes = [P, P, P, I]
@@ -211,6 +213,13 @@ class OracleTable:
 
     def garbage_collect(self, scope=0, sdf_threshold=0.0, weight_decay=0.0) -> int:
         return int(self.lib.vo_garbage_collect(self.h, int(scope), float(sdf_threshold), float(weight_decay)))
+
+    def extract_mesh(self) -> np.ndarray:
+        """-> float32 [n, 3, 3]: triangles of the zero level set (marching tetrahedra, world metres)."""
+        n = int(self.lib.vo_extract_mesh(self.h, None, 0))
+        tris = np.zeros((max(n, 1), 3, 3), np.float32)
+        n = int(self.lib.vo_extract_mesh(self.h, tris.ctypes.data, n))
+        return tris[:n]
 
     def stream_out(self, center, radius, capacity):
         """-> (entries [n,5] int32, voxels [n,512,2] float32) of the blocks farther than radius from center; they leave the table."""

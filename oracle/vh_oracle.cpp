@@ -797,6 +797,89 @@ int vo_stream_in(vo_table* t, const int* entries5, const float* voxels, int coun
     return accepted;
 }
 
+// ---- mesh extraction (k_mesh.cu): marching tetrahedra on the Kuhn subdivision -------------------------------
+namespace {
+inline V3 meshEdge(V3 pa, V3 pb, float sa, float sb) {
+    const float t = sa / (sa - sb);
+    return V3{fmaf(t, pb.x - pa.x, pa.x), fmaf(t, pb.y - pa.y, pa.y), fmaf(t, pb.z - pa.z, pa.z)};
+}
+inline void meshEmit(float* tris, int capacity, int& count, V3 a, V3 b, V3 c, V3 dir) {
+    auto same = [](V3 p, V3 q) { return p.x == q.x && p.y == q.y && p.z == q.z; };
+    if (same(a, b) || same(b, c) || same(a, c)) return;           // slivers of a surface through a grid point
+    const float ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, vx = c.x - a.x, vy = c.y - a.y, vz = c.z - a.z;
+    const float nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+    if (nx * dir.x + ny * dir.y + nz * dir.z < 0.0f) std::swap(b, c);
+    const int i = count++;
+    if (i >= capacity) return;
+    float* o = tris + (size_t)i * 9;
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = b.x; o[4] = b.y; o[5] = b.z; o[6] = c.x; o[7] = c.y; o[8] = c.z;
+}
+}  // namespace
+// 9 floats per triangle; returns the number of triangles the model has (may exceed capacity).
+int vo_extract_mesh(vo_table* t, float* tris, int capacity) {
+    const vo_config& c = t->cfg;
+    static const int tet[6][4] = {{0, 1, 3, 7}, {0, 1, 5, 7}, {0, 2, 3, 7}, {0, 2, 6, 7}, {0, 4, 5, 7}, {0, 4, 6, 7}};
+    int count = 0;
+    const float qnan = std::numeric_limits<float>::quiet_NaN();
+    for (const Entry& e : t->table) {
+        if (e.ptr == kFree) continue;
+        const Entry* nb[8];
+        for (int k = 0; k < 8; ++k)
+            nb[k] = k == 0 ? &e : findEntry(t, I3{e.pos.x + (k & 1), e.pos.y + ((k >> 1) & 1), e.pos.z + ((k >> 2) & 1)});
+        std::vector<float> S(729);
+        for (int p = 0; p < 729; ++p) {
+            const int x = p % 9, y = (p / 9) % 9, z = p / 81;
+            const Entry* b = nb[(x >> 3) | ((y >> 3) << 1) | ((z >> 3) << 2)];
+            float s = qnan;
+            if (b) {
+                const float* vox = t->voxels + ((size_t)b->ptr + ((z & 7) * 64 + (y & 7) * 8 + (x & 7))) * 2;
+                if (vox[1] > 0.0f) s = vox[0];
+            }
+            S[p] = s;
+        }
+        for (int cell = 0; cell < 512; ++cell) {
+            const int cx = cell & 7, cy = (cell >> 3) & 7, cz = cell >> 6;
+            float s[8];
+            V3 pos[8];
+            bool valid = true, anyNeg = false, anyPos = false;
+            for (int k = 0; k < 8; ++k) {
+                const int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
+                s[k] = S[(cz + dz) * 81 + (cy + dy) * 9 + (cx + dx)];
+                valid = valid && (s[k] == s[k]);
+                anyNeg = anyNeg || s[k] < 0.0f;
+                anyPos = anyPos || !(s[k] < 0.0f);
+                pos[k] = V3{(float)(e.pos.x * 8 + cx + dx) * c.voxelSize, (float)(e.pos.y * 8 + cy + dy) * c.voxelSize,
+                            (float)(e.pos.z * 8 + cz + dz) * c.voxelSize};
+            }
+            if (!valid || !anyNeg || !anyPos) continue;
+            for (int ti = 0; ti < 6; ++ti) {
+                int in[4], out[4], ni = 0, no = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const int cc = tet[ti][k];
+                    if (s[cc] < 0.0f) in[ni++] = cc; else out[no++] = cc;
+                }
+                if (ni == 0 || ni == 4) continue;
+                V3 ci{0.f, 0.f, 0.f}, co{0.f, 0.f, 0.f};
+                for (int k = 0; k < ni; ++k) { ci.x += pos[in[k]].x; ci.y += pos[in[k]].y; ci.z += pos[in[k]].z; }
+                for (int k = 0; k < no; ++k) { co.x += pos[out[k]].x; co.y += pos[out[k]].y; co.z += pos[out[k]].z; }
+                const float fi = 1.0f / (float)ni, fo = 1.0f / (float)no;
+                const V3 dir{co.x * fo - ci.x * fi, co.y * fo - ci.y * fi, co.z * fo - ci.z * fi};
+                auto edge = [&](int a, int b) { return a < b ? meshEdge(pos[a], pos[b], s[a], s[b]) : meshEdge(pos[b], pos[a], s[b], s[a]); };
+                if (ni == 1) {
+                    meshEmit(tris, capacity, count, edge(in[0], out[0]), edge(in[0], out[1]), edge(in[0], out[2]), dir);
+                } else if (ni == 3) {
+                    meshEmit(tris, capacity, count, edge(out[0], in[0]), edge(out[0], in[1]), edge(out[0], in[2]), dir);
+                } else {
+                    const V3 a = edge(in[0], out[0]), b = edge(in[0], out[1]), cq = edge(in[1], out[1]), d = edge(in[1], out[0]);
+                    meshEmit(tris, capacity, count, a, b, cq, dir);
+                    meshEmit(tris, capacity, count, a, cq, d, dir);
+                }
+            }
+        }
+    }
+    return count;
+}
+
 // ---- export ---------------------------------------------------------------------------------------
 int vo_num_allocated(vo_table* t) {
     int n = 0;

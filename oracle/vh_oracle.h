@@ -92,6 +92,9 @@ int  vo_garbage_collect(vo_table* t, int scope, float sdfThreshold, float weight
 int  vo_stream_out(vo_table* t, const float* center, float radius, int* entries5, float* voxelsOut, int capacity);
 int  vo_stream_in(vo_table* t, const int* entries5, const float* voxels, int count);
 
+/* Mesh of the zero level set (mirror of vh_extract_mesh): 9 floats per triangle; returns the model's triangle count. */
+int  vo_extract_mesh(vo_table* t, float* tris, int capacity);
+
 /* Table export. entries: 5 ints each (x,y,z,ptr,offset), allocated entries only. */
 int  vo_num_allocated(vo_table* t);
 int  vo_export_entries(vo_table* t, int* entries5, int cap);

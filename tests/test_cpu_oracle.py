@@ -446,3 +446,35 @@ def test_bilateral_front_end_properties(oracle):
     assert np.allclose(t_on.preprocess(flat)[0], t_off.preprocess(flat)[0], rtol=3e-7, atol=0)
     zero_sigma = oracle.OracleTable(small_cfg(bilateralSigmaSpace=0.0, bilateralSigmaRange=0.03, **kw))
     assert np.array_equal(zero_sigma.preprocess(noisy)[0].view(np.uint32), v0.view(np.uint32))
+
+
+def test_mesh_extraction_on_the_analytic_scene(oracle):
+    """Marching tetrahedra over the fused TSDF of scene S1 (plane z = 2.5 + sphere r = 0.5 at z = 2): vertices lie on the
+    analytic surfaces, normals face the camera side, interior edges are shared by exactly two triangles (no cracks)."""
+    cfg = Config(policy=POLICY_FIXED, numBuckets=100003, numVoxelBlocks=8192, truncation=0.06, overflowSlots=1024)
+    for k in (0, 25):           # pose 0 puts the wall EXACTLY on grid points (sdf == 0 at corners): the degenerate case
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        ot = oracle.OracleTable(cfg)
+        v, _, df = ot.preprocess(render(cfg, scenes.scene_S1(), pose))
+        for _ in range(2):
+            ot.fuse_frame(pose, v, df)
+        tris = ot.extract_mesh()
+        assert tris.shape[1:] == (3, 3) and len(tris) > 20000
+        p = tris.reshape(-1, 3).astype(np.float64)
+        d_sphere = np.abs(np.linalg.norm(p - np.array([0.0, 0.0, 2.0]), axis=1) - 0.5)
+        d = np.minimum(d_sphere, np.abs(p[:, 2] - 2.5))
+        assert np.percentile(d, 99) < 0.004 and np.median(d) < 0.001          # voxel size 0.02: sub-voxel accuracy
+        # no triangle with two identical vertices; orientation towards free space = towards the camera
+        n = np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]).astype(np.float64)
+        _, vid = np.unique(tris.reshape(-1, 3), axis=0, return_inverse=True)      # vertex ids by exact coordinates
+        vid = vid.reshape(-1, 3)
+        assert not ((vid[:, 0] == vid[:, 1]) | (vid[:, 1] == vid[:, 2]) | (vid[:, 0] == vid[:, 2])).any()
+        cam = pose[:3, 3].astype(np.float64)
+        good = np.linalg.norm(n, axis=1) > 1e-9
+        facing = np.einsum("ij,ij->i", n[good], cam - tris.mean(axis=1).astype(np.float64)[good]) > 0
+        assert facing.mean() > 0.97           # the rest: silhouette triangles seen edge-on
+        if k == 25:
+            # no cracks: an edge away from the mesh boundary belongs to exactly two triangles (shared vertices are bit-identical)
+            e = np.concatenate([np.sort(vid[:, [0, 1]], axis=1), np.sort(vid[:, [1, 2]], axis=1), np.sort(vid[:, [2, 0]], axis=1)])
+            _, counts = np.unique(e, axis=0, return_counts=True)
+            assert (counts == 2).mean() > 0.97 and (counts > 2).mean() < 0.001   # count 1 = the rim of the observed region

@@ -849,8 +849,9 @@ def test_headless_app_tracks_a_png_sequence(built_library, tmp_path):
         write_depth_png(f, d, filter_type=k % 5)
         assert np.array_equal(read_depth(f), d)
         files.append(str(f))
-    r = subprocess.run([str(HOST_DEMO), "--frames", *files], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([str(HOST_DEMO), "--frames", *files, "--mesh", str(tmp_path / "model.ply")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
+    assert "mesh: " in r.stdout and (tmp_path / "model.ply").read_bytes().startswith(b"ply\nformat binary_little_endian 1.0")
     lines = [l for l in r.stdout.splitlines() if l.startswith("frame ")]
     assert len(lines) == 6
     t_last = np.array([float(x) for x in lines[-1].split("(")[1].rstrip(")").split()])
@@ -900,3 +901,43 @@ def test_bilateral_front_end_helps_tracking_under_noise(built_library, oracle):
         errs[name] = float(np.max(np.abs(pose[:3, 3] - poses[-1][:3, 3])))
         assert ctx.stats().dropped == 0
     assert errs["bilateral"] < errs["raw"] and errs["bilateral"] < 0.01, errs
+
+
+# ---- mesh extraction ---------------------------------------------------------------------
+def _sorted_tris(t):
+    a = np.ascontiguousarray(t, np.float32).reshape(-1, 9).view(np.uint32)
+    return a[np.lexsort(a.T[::-1])]
+
+
+@pytest.mark.parametrize("chained", [False, True])
+def test_mesh_extraction_matches_oracle(built_library, oracle, chained, tmp_path):
+    """Same triangles, bit for bit, as the oracle's marching tetrahedra (order aside); neighbour blocks found through chains too."""
+    kw = dict(numBuckets=64, bucketSize=2, attachedLinkedListSize=64) if chained else {}
+    cfg = fixed_cfg(numVoxelBlocks=4096, width=160, height=120, fx=517.3 / 4, fy=516.5 / 4, cx=318.6 / 4, cy=255.3 / 4, **kw)
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    for k in (0, 12):
+        pose = scenes.trajectory_C2(k).astype(np.float32)
+        depth = render(cfg, scenes.scene_S1(), pose)
+        ov, _, odf = ot.preprocess(depth)
+        v, n, df = gpu_preprocess(ctx, depth)
+        ot.fuse_frame(pose, ov, odf)
+        ctx.fuse_frame(pose, v, n, df)
+    want = ot.extract_mesh()
+    got = ctx.extract_mesh()
+    assert len(got) == len(want) > 5000
+    assert np.array_equal(_sorted_tris(got.cpu().numpy()), _sorted_tris(want))
+    # a buffer that is too small is filled to its capacity and the true count is still reported
+    small = torch.zeros((100, 3, 3), device="cuda")
+    n = C.c_int(0)
+    assert ctx.lib.vh_extract_mesh(ctx.handle, small.data_ptr(), 100, C.byref(n), None) == L.VH_OK and n.value == len(want)
+    assert small.abs().sum().item() > 0
+    # PLY round trip of the header and sizes
+    cnt = ctx.save_mesh_ply(tmp_path / "m.ply", got)
+    blob = (tmp_path / "m.ply").read_bytes()
+    head, body = blob.split(b"end_header\n", 1)
+    assert f"element vertex {3 * cnt}".encode() in head and f"element face {cnt}".encode() in head
+    assert len(body) == cnt * 36 + cnt * 13
+    assert np.array_equal(np.frombuffer(body[: cnt * 36], np.float32), got.cpu().numpy().reshape(-1))
+    # an empty model has an empty mesh
+    assert len(Context(cfg).extract_mesh()) == 0

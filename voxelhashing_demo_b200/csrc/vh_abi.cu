@@ -533,6 +533,29 @@ int vh_load(vh_context* c, const char* path) {
     fclose(f);
     return ok ? VH_OK : fail(VH_ERR_INVALID, "vh_load: short read");
 }
+int vh_extract_mesh(vh_context* c, float* d_tris, int capacity, int* h_count, vh_stream s) {
+    if (!c || !h_count || capacity < 0 || (capacity > 0 && !d_tris)) return fail(VH_ERR_INVALID, "vh_extract_mesh: bad argument");
+    VH_CUDA(launch_extract_mesh(c, d_tris, capacity, &c->v.ctr->meshCount, S(s)));
+    VH_CUDA(cudaMemcpyAsync(h_count, &c->v.ctr->meshCount, sizeof(int), cudaMemcpyDeviceToHost, S(s)));
+    VH_CUDA(cudaStreamSynchronize(S(s)));
+    return VH_OK;
+}
+int vh_save_mesh_ply(const char* path, const float* tris, int count) {
+    if (!path || count < 0 || (count > 0 && !tris)) return fail(VH_ERR_INVALID, "vh_save_mesh_ply: bad argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(VH_ERR_INVALID, "vh_save_mesh_ply: cannot open file");
+    fprintf(f, "ply\nformat binary_little_endian 1.0\ncomment libvh_b200 marching tetrahedra\nelement vertex %d\n"
+               "property float x\nproperty float y\nproperty float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n",
+            count * 3, count);
+    bool ok = count == 0 || fwrite(tris, sizeof(float) * 9, (size_t)count, f) == (size_t)count;
+    for (int i = 0; ok && i < count; ++i) {
+        const unsigned char n = 3;
+        const int idx[3] = {3 * i, 3 * i + 1, 3 * i + 2};
+        ok = fwrite(&n, 1, 1, f) == 1 && fwrite(idx, sizeof(int), 3, f) == 3;
+    }
+    fclose(f);
+    return ok ? VH_OK : fail(VH_ERR_INVALID, "vh_save_mesh_ply: short write");
+}
 // The reference's text dump, SDFRenderer.cpp:90-108: count, then per visible entry pos/ptr/offset and 512 sdf values.
 int vh_dump_text(vh_context* c, const char* path) {
     if (!c || !path) return fail(VH_ERR_INVALID, "vh_dump_text: null argument");

@@ -38,7 +38,7 @@ struct Counters {
     int heapLow;                  // lowest heapCounter ever reached: block ids <= heapLow were never handed out
     int gcFreed;                  // blocks released by the last garbage-collection pass
     int streamCount;              // blocks moved by the last stream-out / stream-in pass
-    int pad0;
+    int meshCount;                // triangles produced by the last mesh extraction
 };
 
 struct FrameParams {
@@ -147,6 +147,7 @@ cudaError_t launch_reduce_corr(vh_context* c, const float4* corr, const float4* 
 cudaError_t launch_linear_system_300(vh_context* c, const float4* in, const float4* corr, const float4* corrN,
                                      float* d_out, cudaStream_t s);
 cudaError_t launch_raycast(vh_context* c, float4* verts, float4* normals, cudaStream_t s);
+cudaError_t launch_extract_mesh(vh_context* c, float* tris, int capacity, int* d_counter, cudaStream_t s);
 cudaError_t launch_export_entries(vh_context* c, VoxelEntry* d_out, int* d_count, cudaStream_t s);
 
 }  // namespace vh

@@ -323,6 +323,21 @@ class Context:
         return {(int(e["x"]), int(e["y"]), int(e["z"])): self.export_block(int(e["ptr"])).view(np.float32).reshape(512, 2)
                 for e in self.export_entries() if e["ptr"] >= 0}
 
+    def extract_mesh(self, stream=None):
+        """Zero level set as a triangle soup: float32 CUDA tensor [n, 3, 3] (world metres, normals towards free space)."""
+        import torch
+
+        n = C.c_int(0)
+        L.check(self.lib.vh_extract_mesh(self._h, None, 0, C.byref(n), _stream(stream)), "vh_extract_mesh")
+        tris = torch.empty((max(n.value, 1), 3, 3), dtype=torch.float32, device="cuda")
+        L.check(self.lib.vh_extract_mesh(self._h, _ptr(tris), n.value, C.byref(n), _stream(stream)), "vh_extract_mesh")
+        return tris[: n.value]
+
+    def save_mesh_ply(self, path, tris=None):
+        t = (self.extract_mesh() if tris is None else tris).detach().cpu().contiguous().numpy()
+        L.check(self.lib.vh_save_mesh_ply(str(path).encode(), t.ctypes.data, int(t.shape[0])), "vh_save_mesh_ply")
+        return int(t.shape[0])
+
     def save(self, path: str):
         L.check(self.lib.vh_save(self._h, str(path).encode()), "vh_save")
 

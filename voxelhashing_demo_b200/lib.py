@@ -107,7 +107,7 @@ HANDLE_SYMBOLS = [
     "vh_icp_set_delta", "vh_set_peers", "vh_peer_bytes", "vh_icp_align_rows", "vh_icp_delta_device", "vh_pose_compose", "vh_icp_reduce_corr", "vh_find_correspondences",
     "vh_jacobians", "vh_raycast", "vh_export_entries", "vh_export_compact", "vh_export_block",
     "vh_compact_table_device", "vh_compact_counter_device", "vh_voxel_blocks_device", "vh_save", "vh_load",
-    "vh_dump_text", "vh_depth_read", "vh_depth_free", "vh_depth_write_png", "vh_depth_last_error",
+    "vh_dump_text", "vh_extract_mesh", "vh_save_mesh_ply", "vh_depth_read", "vh_depth_free", "vh_depth_write_png", "vh_depth_last_error",
     "vh_pipeline_create", "vh_pipeline_flush", "vh_pipeline_destroy", "vh_pipeline_reset", "vh_pipeline_push_device",
     "vh_pipeline_push_host", "vh_pipeline_pose", "vh_pipeline_pose_device", "vh_pipeline_pose_async", "vh_pipeline_depthf", "vh_pipeline_maps", "vh_pipeline_launches",
 ]
@@ -178,6 +178,8 @@ def load_library() -> C.CDLL:
     lib.vh_save.argtypes = [P, C.c_char_p]
     lib.vh_load.argtypes = [P, C.c_char_p]
     lib.vh_dump_text.argtypes = [P, C.c_char_p]
+    lib.vh_extract_mesh.argtypes = [P, P, C.c_int, C.POINTER(C.c_int), P]
+    lib.vh_save_mesh_ply.argtypes = [C.c_char_p, P, C.c_int]
     lib.vh_depth_read.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.vh_depth_free.argtypes = [C.POINTER(C.c_uint16)]
     lib.vh_depth_free.restype = None
