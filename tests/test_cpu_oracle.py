@@ -478,3 +478,50 @@ def test_mesh_extraction_on_the_analytic_scene(oracle):
             e = np.concatenate([np.sort(vid[:, [0, 1]], axis=1), np.sort(vid[:, [1, 2]], axis=1), np.sort(vid[:, [2, 0]], axis=1)])
             _, counts = np.unique(e, axis=0, return_counts=True)
             assert (counts == 2).mean() > 0.97 and (counts > 2).mean() < 0.001   # count 1 = the rim of the observed region
+
+
+def test_table_invariants_under_random_maintenance(oracle):
+    """Random interleaving of fusion, garbage collection and streaming on a tiny, chain-heavy table: keys stay unique, every
+    live key is found again by lookup, and the heap neither leaks nor double-frees."""
+    cfg = small_cfg(policy=POLICY_FIXED, numBuckets=32, bucketSize=2, attachedLinkedListSize=64, overflowSlots=4096,
+                    numVoxelBlocks=2048, truncation=0.06)
+    rng = np.random.default_rng(2024)
+    ot = oracle.OracleTable(cfg)
+    frames = {}
+    parked = []                                               # (entries, voxels) streamed out and not yet back
+
+    def check():
+        ent = ot.entries()
+        keys = entries_to_set(ent)
+        assert len(keys) == len(ent), "duplicate key"
+        assert ot.heap_counter() == cfg.numVoxelBlocks - 1 - len(ent), "heap leak / double free"
+        assert len({int(e[3]) for e in ent}) == len(ent), "two keys share a voxel block"
+        for e in ent[:: max(1, len(ent) // 25)]:
+            assert ot.block(int(e[0]), int(e[1]), int(e[2])) is not None, "live key not found by lookup"
+        return keys
+
+    for step in range(60):
+        op = rng.integers(0, 5)
+        if op <= 1 or step == 0:                              # fuse a frame from somewhere along the trajectory
+            k = int(rng.integers(0, 40))
+            if k not in frames:
+                pose = scenes.trajectory_C2(k).astype(np.float32)
+                v, _, df = ot.preprocess(render(cfg, scenes.scene_S1(), pose))
+                frames[k] = (pose, v, df)
+            rep, _, _ = ot.fuse_frame(*frames[k])
+            assert rep.dropped == 0
+        elif op == 2:                                         # starve + collect, random scope / strength
+            ot.garbage_collect(scope=int(rng.integers(0, 2)), sdf_threshold=float(rng.choice([0.0, 0.02, 0.05])),
+                               weight_decay=float(rng.choice([0.0, 1.0, 3.0, 1e9])))
+        elif op == 3:                                         # park everything outside a random sphere
+            c = rng.uniform(-1.0, 1.0, 3) + np.array([0.0, 0.0, 2.0])
+            ent, vox = ot.stream_out(c, float(rng.uniform(0.3, 1.5)), int(rng.choice([8, 4096])))
+            if len(ent):
+                parked.append((ent, vox))
+        elif parked:                                          # bring one parked batch back (merging where re-observed)
+            ent, vox = parked.pop(int(rng.integers(0, len(parked))))
+            before = check()
+            assert ot.stream_in(ent, vox) == len(ent)
+            assert check() == before | entries_to_set(ent)
+        check()
+    assert len(frames) > 5

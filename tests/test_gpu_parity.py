@@ -941,3 +941,56 @@ def test_mesh_extraction_matches_oracle(built_library, oracle, chained, tmp_path
     assert np.array_equal(np.frombuffer(body[: cnt * 36], np.float32), got.cpu().numpy().reshape(-1))
     # an empty model has an empty mesh
     assert len(Context(cfg).extract_mesh()) == 0
+
+
+def test_differential_fuzz_of_table_maintenance(built_library, oracle):
+    """The same random interleaving of fusion / garbage collection / stream-out / stream-in on the GPU and on the oracle,
+    on a tiny chain-heavy table; after EVERY step the two models must be identical (keys, heap counter, voxels bit for bit)."""
+    cfg = fixed_cfg(numBuckets=32, bucketSize=2, attachedLinkedListSize=64, overflowSlots=4096, numVoxelBlocks=2048,
+                    width=160, height=120, fx=517.3 / 4, fy=516.5 / 4, cx=318.6 / 4, cy=255.3 / 4)
+    rng = np.random.default_rng(99)
+    ot = oracle.OracleTable(cfg)
+    ctx = Context(cfg)
+    frames, parked = {}, []
+    ops = []
+    for step in range(45):
+        op = int(rng.integers(0, 5))
+        if op <= 1 or step == 0:
+            k = int(rng.integers(0, 40))
+            if k not in frames:
+                pose = scenes.trajectory_C2(k).astype(np.float32)
+                depth = render(cfg, scenes.scene_S1(), pose)
+                ov, _, odf = ot.preprocess(depth)
+                v, n, df = gpu_preprocess(ctx, depth)
+                frames[k] = (pose, ov, odf, v, n, df)
+            pose, ov, odf, v, n, df = frames[k]
+            ot.fuse_frame(pose, ov, odf)
+            ctx.fuse_frame(pose, v, n, df)
+            ops.append(f"fuse {k}")
+        elif op == 2:
+            scope = int(rng.integers(0, 2))
+            thr, dec = float(rng.choice([0.0, 0.02, 0.05])), float(rng.choice([0.0, 1.0, 3.0, 1e9]))
+            freed = ot.garbage_collect(scope=scope, sdf_threshold=thr, weight_decay=dec)
+            ctx.garbage_collect(scope, thr, dec)
+            assert ctx.stats().lastFreed == freed, ops
+            ops.append(f"gc {scope} {thr} {dec} -> {freed}")
+        elif op == 3:
+            c = rng.uniform(-1.0, 1.0, 3) + np.array([0.0, 0.0, 2.0])
+            r = float(rng.uniform(0.3, 1.5))
+            oent, ovox = ot.stream_out(c, r, 4096)
+            ent, vox = ctx.stream_out(c, r, 4096, pinned_host=bool(step & 1))
+            assert len(ent) == len(oent), ops
+            if len(oent):
+                parked.append((oent, ovox, ent, vox))
+            ops.append(f"out {len(oent)}")
+        elif parked:
+            oent, ovox, ent, vox = parked.pop(int(rng.integers(0, len(parked))))
+            assert ot.stream_in(oent, ovox) == len(oent) == ctx.stream_in(ent, vox), ops
+            ops.append(f"in {len(oent)}")
+        else:
+            continue
+        try:
+            _same_model(ctx, ot)
+        except AssertionError as e:
+            raise AssertionError(f"models diverged after {ops}") from e
+    assert sum(o.startswith("gc") for o in ops) >= 3 and sum(o.startswith("out") for o in ops) >= 3
