@@ -142,3 +142,44 @@ def test_build_is_safe_from_several_processes_and_ignores_mtimes(built_library, 
         assert p.returncode == 0, err.decode()[-2000:]
     assert (_build.LIB.stat().st_ino, _build.LIB.stat().st_size) == before, "the library was re-linked although nothing changed"
     L.load_library()
+
+
+def test_host_se3_functions_match_the_oracle(built_library, oracle, tmp_path):
+    """SE3Exp / SE3Log / updateTransform of the C++ host surface (ref SE3.h:6-8, SE3.cpp:4-26) are pure host code:
+    a small C++ program linked against the library, run here without a GPU, must agree with the oracle's closed forms."""
+    from voxelhashing_demo_b200 import _build
+
+    src = tmp_path / "se3.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "SE3.h"
+int main() {
+    const float tw[3][6] = {{0, 0, 0, 0, 0, 1.57079632679f}, {0.01f, -0.004f, 0.002f, 0.003f, -0.002f, 0.001f}, {0.3f, -0.2f, 0.5f, 0.4f, 0.1f, -0.7f}};
+    for (int k = 0; k < 3; ++k) {
+        Vector6f t; for (int i = 0; i < 6; ++i) t(i) = tw[k][i];
+        Matrix4x4f M = SE3Exp(t);
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) std::printf("%.9g ", M(r, c));
+        Vector6f back = SE3Log(M);
+        for (int i = 0; i < 6; ++i) std::printf("%.9g ", back(i));
+        std::printf("\n");
+    }
+    Vector6f a, b; for (int i = 0; i < 6; ++i) { a(i) = tw[1][i]; b(i) = tw[2][i]; }
+    Vector6f u = updateTransform(a, b);
+    for (int i = 0; i < 6; ++i) std::printf("%.9g ", u(i));
+    std::printf("\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "se3"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", str(src), "-o", str(exe),
+                    "-L", str(_build.PKG), "-lvh_b200", f"-Wl,-rpath,{_build.PKG}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    twists = [[0, 0, 0, 0, 0, np.pi / 2], [0.01, -0.004, 0.002, 0.003, -0.002, 0.001], [0.3, -0.2, 0.5, 0.4, 0.1, -0.7]]
+    for line, tw in zip(out[:3], twists):
+        vals = np.array([float(x) for x in line.split()])
+        M, back = vals[:16].reshape(4, 4), vals[16:]
+        assert np.allclose(M, oracle.se3_exp(tw), atol=2e-6)
+        assert np.allclose(back, tw, atol=2e-6)                                   # log(exp(t)) = t
+    u = np.array([float(x) for x in out[3].split()])
+    want = oracle.se3_log(oracle.se3_exp(twists[1]).astype(np.float64) @ oracle.se3_exp(twists[2]).astype(np.float64))
+    assert np.allclose(u, want, atol=5e-6)                                        # estimate <- log(exp(x) exp(estimate)), Solver.cpp:110-111
