@@ -43,8 +43,19 @@ class VoIcpSystem(C.Structure):
 
 
 def build_oracle(force: bool = False) -> Path:
-    if force or not ORACLE_LIB.exists() or ORACLE_LIB.stat().st_mtime < (HERE / "vh_oracle.cpp").stat().st_mtime:
-        subprocess.run(["make", "-C", str(HERE), "oracle"], check=True, capture_output=True)
+    """Rebuild decisions go by a content stamp (the snapshot sent to the GPU box does not preserve file times), under a
+    file lock (several processes may import the checker at once)."""
+    import fcntl
+    import hashlib
+
+    want = hashlib.sha256((HERE / "vh_oracle.cpp").read_bytes() + (HERE / "vh_oracle.h").read_bytes()
+                          + (HERE / "Makefile").read_bytes()).hexdigest()
+    stamp = HERE / ".libvh_oracle.stamp"
+    with open(HERE / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if force or not ORACLE_LIB.exists() or not stamp.exists() or stamp.read_text() != want:
+            subprocess.run(["make", "-B", "-C", str(HERE), "oracle"], check=True, capture_output=True)
+            stamp.write_text(want)
     return ORACLE_LIB
 
 
