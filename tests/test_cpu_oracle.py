@@ -525,3 +525,25 @@ def test_table_invariants_under_random_maintenance(oracle):
             assert check() == before | entries_to_set(ent)
         check()
     assert len(frames) > 5
+
+
+def test_golden_fixed_policy_definition(oracle):
+    """The Fixed policy's arithmetic against its own history: tests/golden/fixed_small.npz holds two
+    small input frames and hashes of everything the oracle derives from them (table, voxels, mesh, ICP delta, raycast,
+    garbage collection, bilateral maps).  A deliberate change of the definition regenerates the fixture with
+    tests/golden/make_fixed_golden.py; anything else that trips this test is an accident."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_fixed_golden", GOLDEN / "make_fixed_golden.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(GOLDEN / "fixed_small.npz")
+    got = mod.run([g["depth0"], g["depth1"]], [g["pose0"], g["pose1"]])
+    for k, v in got.items():
+        want = g[k]
+        if isinstance(v, str):
+            assert v == str(want), k
+        elif isinstance(v, np.ndarray):
+            assert np.array_equal(v.view(np.uint32), want.view(np.uint32)), k
+        else:
+            assert v == int(want), k

@@ -994,3 +994,43 @@ def test_differential_fuzz_of_table_maintenance(built_library, oracle):
         except AssertionError as e:
             raise AssertionError(f"models diverged after {ops}") from e
     assert sum(o.startswith("gc") for o in ops) >= 3 and sum(o.startswith("out") for o in ops) >= 3
+
+
+def test_gpu_reproduces_the_fixed_policy_fixture(built_library, oracle):
+    """tests/golden/fixed_small.npz (outputs of the oracle on two stored frames): the kernels give the same hashes for the
+    table, the voxels, the mesh, the garbage-collected key set and the bilateral maps, and the same ICP delta to 1e-4."""
+    import hashlib
+    import importlib.util
+
+    from pathlib import Path
+
+    gold_dir = Path(__file__).resolve().parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_fixed_golden", gold_dir / "make_fixed_golden.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(gold_dir / "fixed_small.npz")
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    cfg = mod.config()
+    ctx = Context(cfg)
+    maps = []
+    for i in range(2):
+        v, n, df = gpu_preprocess(ctx, g[f"depth{i}"])
+        maps.append((v, n))
+        ctx.fuse_frame(g[f"pose{i}"], v, n, df)
+    ent = ctx.export_entries()
+    keys = np.stack([ent["x"], ent["y"], ent["z"]], axis=1).astype(np.int32)
+    order = np.lexsort(keys.T[::-1])
+    blocks = ctx.block_dict()
+    assert len(keys) == int(g["num_blocks"]) and sha(keys[order]) == str(g["keys_sha"])
+    assert sha(np.stack([blocks[tuple(int(c) for c in k)] for k in keys[order]])) == str(g["voxels_sha"])
+    tris = ctx.extract_mesh().cpu().numpy().reshape(-1, 9).view(np.uint32)
+    assert len(tris) == int(g["num_triangles"]) and sha(tris[np.lexsort(tris.T[::-1])]) == str(g["mesh_sha"])
+    ctx.icp_reset(True)
+    ctx.icp_align(maps[1][0], maps[1][1], maps[0][0], maps[0][1], 5)
+    assert np.max(np.abs(ctx.icp_get()[0] - g["icp_delta"])) < 1e-4
+    ctx.garbage_collect(L.VH_GC_ALL, 0.03, 1.0)
+    assert ctx.stats().lastFreed == int(g["gc_freed"])
+    assert sha(np.array(sorted(entries_to_set(ctx.export_entries())), np.int32)) == str(g["gc_keys_sha"])
+    b = Context(mod.config(bilateralSigmaSpace=1.5, bilateralSigmaRange=0.03))
+    bv, bn, _ = gpu_preprocess(b, g["depth0"])
+    assert sha(np.concatenate([bv.cpu().numpy(), bn.cpu().numpy()], axis=1)) == str(g["bilateral_sha"])
