@@ -104,7 +104,8 @@ def test_sass_has_the_blackwell_paths(built_library):
 
 def test_invalid_configs_are_rejected_before_touching_a_device(built_library):
     lib = L.load_library()
-    for kw in (dict(numBuckets=0), dict(numVoxelBlocks=0), dict(voxelSize=0.0), dict(width=0), dict(numVoxelBlocks=5_000_000)):
+    for kw in (dict(numBuckets=0), dict(numVoxelBlocks=0), dict(voxelSize=0.0), dict(width=0), dict(numVoxelBlocks=5_000_000),
+               dict(partCount=4, partRank=4), dict(partCount=2, partRank=-1)):
         h = C.c_void_p()
         c = Config(**kw).to_c()
         assert lib.vh_create(C.byref(c), C.byref(h)) == L.VH_ERR_INVALID and not h, kw

@@ -475,7 +475,7 @@ def test_pipeline_tracks_synthetic_trajectory(built_library, oracle):
     for r in results[1:]:                                   # plain launches and the overlapped schedule: same bits
         assert np.array_equal(bits(results[0][0]), bits(r[0]))
         assert results[0][1:3] == r[1:3]
-        assert results[0][3] == r[3] == 40 + 39 * (10 + 1) + 40 * 3 + 1
+        assert results[0][3] == r[3] == 40 + 39 * (1 + 1) + 40 * 3 + 1      # preprocess, Align + pose, fusion, first pose
     for m in models[1:]:
         exact, _ = compare_blocks(m, models[0])
         assert exact

@@ -118,30 +118,36 @@ __global__ void __launch_bounds__(128, 8) k_stream_out(View v, float cx, float c
     const int N = (int)v.numVoxelBlocks;
     const int firstId = max(v.ctr->heapLow + 1, 0);
     for (int id = firstId + blockIdx.x; id < N; id += gridDim.x) {
-        const int4 info = v.blockInfo[id];
-        if (info.w < 0) continue;
-        // centre of the block: voxel indices 8b .. 8b+7 sit at (8b + k) * voxelSize
-        const float dx = ((float)(info.x * 8) + 3.5f) * v.voxelSize - cx;
-        const float dy = ((float)(info.y * 8) + 3.5f) * v.voxelSize - cy;
-        const float dz = ((float)(info.z * 8) + 3.5f) * v.voxelSize - cz;
-        if (!(dx * dx + dy * dy + dz * dz > radius2)) continue;             // CTA-uniform
+        // Thread 0 ALONE reads the owner record, decides and releases; the decision reaches the other warps through
+        // shared memory.  (A CTA-wide load of blockInfo[id] raced with thread 0's releaseBlock(), which rewrites that
+        // record: a late warp could see w = -1, skip the barriers below and leave sectors neither copied nor zeroed.)
         if (threadIdx.x == 0) {
-            int dst = atomicAdd(&v.ctr->streamCount, 1);
-            if (dst >= capacity) { atomicSub(&v.ctr->streamCount, 1); dst = -1; }   // buffer full: the block stays
-            else {
-                VoxelEntry e;
-                e.pos = make_int3(info.x, info.y, info.z);
-                e.ptr = dst * 512;
-                e.offset = 0;
-                entriesOut[dst] = e;
-                releaseBlock(v, id, info);
+            int dst = -1;
+            const int4 info = v.blockInfo[id];
+            if (info.w >= 0) {
+                // centre of the block: voxel indices 8b .. 8b+7 sit at (8b + k) * voxelSize
+                const float dx = ((float)(info.x * 8) + 3.5f) * v.voxelSize - cx;
+                const float dy = ((float)(info.y * 8) + 3.5f) * v.voxelSize - cy;
+                const float dz = ((float)(info.z * 8) + 3.5f) * v.voxelSize - cz;
+                if (dx * dx + dy * dy + dz * dz > radius2) {
+                    dst = atomicAdd(&v.ctr->streamCount, 1);
+                    if (dst >= capacity) { atomicSub(&v.ctr->streamCount, 1); dst = -1; }   // buffer full: the block stays
+                    else {
+                        VoxelEntry e;
+                        e.pos = make_int3(info.x, info.y, info.z);
+                        e.ptr = dst * 512;
+                        e.offset = 0;
+                        entriesOut[dst] = e;
+                        releaseBlock(v, id, info);
+                    }
+                }
             }
             sDst = dst;
         }
         __syncthreads();
         const int dst = sDst;
         __syncthreads();
-        if (dst < 0) continue;
+        if (dst < 0) continue;                                               // CTA-uniform
         Voxel* sector = v.voxels + (size_t)id * 512 + threadIdx.x * 4;
         F8g x = ldSector(sector);
         float4* out = reinterpret_cast<float4*>(voxelsOut + (size_t)dst * 512 + threadIdx.x * 4);   // may be host memory: plain stores

@@ -126,6 +126,8 @@ int vh_create(const vh_config* cfg, vh_context** out) {
         return fail(VH_ERR_INVALID, "vh_create: bad table/image parameters (voxelBlockSize must be 8)");
     if ((unsigned long long)cfg->table.numVoxelBlocks * 512ull >= 0x7fffffffull)
         return fail(VH_ERR_INVALID, "vh_create: numVoxelBlocks*512 must fit the reference's int ptr");
+    if (cfg->partCount > 1 && (cfg->partRank < 0 || cfg->partRank >= cfg->partCount))
+        return fail(VH_ERR_INVALID, "vh_create: partRank must be in [0, partCount)");
     if (vh_device_count() == 0) return fail(VH_ERR_NO_DEVICE, "vh_create: no CUDA device (this library has no CPU fallback)");
     vh_context* c = new vh_context();
     memset(static_cast<void*>(c), 0, sizeof(*c));
@@ -172,6 +174,9 @@ int vh_create(const vh_config* cfg, vh_context** out) {
         c->icp = static_cast<IcpState*>(p);
     }
     chk(devAlloc(c, &c->icpPartials, (size_t)kIcpMaxBlocks * 32));
+    chk(devAlloc(c, &c->icpLL, (size_t)2 * kIcpMaxBlocks * 32));
+    if (e == cudaSuccess) chk(cudaMemset(c->icpLL, 0, sizeof(unsigned long long) * 2 * kIcpMaxBlocks * 32));   // sequence 0 = never written
+    if (const char* env = getenv("VH_ICP_CTAS")) c->icpCtas = atoi(env);
     {
         const size_t tiles = (size_t)((cfg->width + 7) / 8) * ((cfg->height + 7) / 8);
         chk(devAlloc(c, &c->tileMin, tiles));
@@ -195,7 +200,7 @@ void vh_destroy(vh_context* c) {
     cudaFree(c->v.entries); cudaFree(c->v.chain); cudaFree(c->v.mutex); cudaFree(c->v.heap);
     cudaFree(c->v.blockInfo); cudaFree(c->v.voxels); cudaFree(c->v.compact16); cudaFree(c->v.compact20);
     cudaFree(const_cast<float*>(c->v.bilatLut)); cudaFree(c->v.depthSmooth);
-    cudaFree(c->v.ctr); cudaFree(c->frame); cudaFree(c->icp); cudaFree(c->icpPartials); cudaFree(c->tileMin); cudaFree(c->tileMax);
+    cudaFree(c->v.ctr); cudaFree(c->frame); cudaFree(c->icp); cudaFree(c->icpPartials); cudaFree(c->icpLL); cudaFree(c->tileMin); cudaFree(c->tileMax);
     delete c;
 }
 
@@ -346,8 +351,7 @@ int vh_icp_align(vh_context* c, const float4* in, const float4* inN, const float
                  vh_stream s) {
     if (!c || !in || !tg || !tgN) return fail(VH_ERR_INVALID, "vh_icp_align: null argument");
     if (iterations <= 0) iterations = c->cfg.icpIterations;
-    for (int it = 0; it < iterations; ++it)                      // CameraTracking.cpp:35
-        VH_CUDA(launch_icp_iter_ex(c, in, inN, tg, tgN, 0, c->v.H, nullptr, true, it == 0, it > 0, S(s)));
+    VH_CUDA(launch_icp_align(c, in, inN, tg, tgN, 0, c->v.H, iterations, false, S(s)));   // CameraTracking.cpp:35-67, one launch
     return VH_OK;
 }
 int vh_icp_reduce(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN, int row0, int row1,
@@ -375,7 +379,7 @@ int vh_icp_align_rows(vh_context* c, const float4* in, const float4* inN, const 
     if (!c || !in || !tg || !tgN) return fail(VH_ERR_INVALID, "vh_icp_align_rows: null argument");
     if (row0 < 0 || row1 > c->v.H || row0 > row1) return fail(VH_ERR_INVALID, "vh_icp_align_rows: bad row range");
     if (iterations <= 0) iterations = c->cfg.icpIterations;
-    for (int it = 0; it < iterations; ++it) VH_CUDA(launch_icp_iter_peer(c, in, inN, tg, tgN, row0, row1, it == 0, S(s)));
+    VH_CUDA(launch_icp_align(c, in, inN, tg, tgN, row0, row1, iterations, c->peers.world > 1, S(s)));
     return VH_OK;
 }
 
@@ -428,6 +432,8 @@ int vh_jacobians(vh_context* c, const float4* corr, const float4* corrN, float* 
 int vh_raycast(vh_context* c, float4* d_verts, float4* d_normals, vh_stream s) {
     if (!c || !d_verts || !d_normals) return fail(VH_ERR_INVALID, "vh_raycast: null argument");
     if (c->cfg.policy != VH_POLICY_FIXED) return fail(VH_ERR_INVALID, "vh_raycast: Fixed policy only (the RefExact TSDF is not a surface)");
+    if (c->v.partCount > 1)      // a rank holds ~1/P of the blocks: trilinear samples and gradients fail at every face owned elsewhere
+        return fail(VH_ERR_UNSUPPORTED, "vh_raycast: not defined on a partitioned context (no halo exchange); raycast the merged model");
     VH_CUDA(cudaMemsetAsync(&c->v.ctr->compactCount, 0, sizeof(int), S(s)));
     VH_CUDA(launch_compact(c, S(s)));                    // the visible list of the CURRENT pose feeds the ray intervals
     VH_CUDA(launch_raycast(c, d_verts, d_normals, S(s)));
@@ -503,6 +509,9 @@ int vh_save(vh_context* c, const char* path) {
     fclose(f);
     return ok ? VH_OK : fail(VH_ERR_INVALID, "vh_save: short write");
 }
+// The file is parsed and validated into host staging buffers first; the device is only touched once everything has
+// been read, so a short or inconsistent file leaves the live table as it was.  Only the TABLE counters are restored:
+// the ICP exchange sequence (icpSeq) belongs to the running context (the peers' mailboxes hold its numbers).
 int vh_load(vh_context* c, const char* path) {
     if (!c || !path) return fail(VH_ERR_INVALID, "vh_load: null argument");
     FILE* f = fopen(path, "rb");
@@ -515,26 +524,50 @@ int vh_load(vh_context* c, const char* path) {
         fclose(f);
         return fail(VH_ERR_INVALID, "vh_load: checkpoint does not match this context's geometry");
     }
+    if (h.policy != (unsigned)c->cfg.policy || h.voxelSize != c->v.voxelSize) {
+        fclose(f);
+        return fail(VH_ERR_INVALID, "vh_load: checkpoint was written with another arithmetic policy or voxel size");
+    }
     const size_t slots = (size_t)c->v.numSlots + c->v.overflowSlots, N = c->v.numVoxelBlocks;
-    std::vector<char> buf;
-    auto get = [&](void* d, size_t bytes) {
-        buf.resize(bytes);
-        if (fread(buf.data(), 1, bytes, f) != bytes) return false;
-        return cudaMemcpy(d, buf.data(), bytes, cudaMemcpyHostToDevice) == cudaSuccess;
-    };
-    cudaDeviceSynchronize();
-    ok = get(c->v.entries, slots * sizeof(int4)) && get(c->v.chain, slots * sizeof(int)) && get(c->v.heap, N * sizeof(unsigned)) &&
-         get(c->v.blockInfo, N * sizeof(int4));
+    // counters index heap[] and the overflow arena: range-check them before they reach the device
+    if (ctr.heapCounter < -1 || ctr.heapCounter >= (int)N || ctr.heapLow < -1 || ctr.heapLow >= (int)N ||
+        ctr.overflowUsed < 0 || (unsigned)ctr.overflowUsed > c->v.overflowSlots) {
+        fclose(f);
+        return fail(VH_ERR_INVALID, "vh_load: checkpoint counters out of range");
+    }
     int first = std::min(ctr.heapLow, ctr.heapCounter) + 1;
     if (first < 0) first = 0;
-    if (ok) ok = cudaMemset(c->v.voxels, 0, N * 512 * sizeof(Voxel)) == cudaSuccess;
-    if (ok && (size_t)first < N) ok = get(c->v.voxels + (size_t)first * 512, (N - first) * 512 * sizeof(Voxel));
-    if (ok) ok = cudaMemcpy(c->v.ctr, &ctr, sizeof(ctr), cudaMemcpyHostToDevice) == cudaSuccess;
+    const size_t voxBytes = (size_t)first < N ? (N - first) * 512 * sizeof(Voxel) : 0;
+    std::vector<char> entries(slots * sizeof(int4)), chain(slots * sizeof(int)), heap(N * sizeof(unsigned)), info(N * sizeof(int4)), vox;
+    auto get = [&](std::vector<char>& b) { return b.empty() || fread(b.data(), 1, b.size(), f) == b.size(); };
+    ok = get(entries) && get(chain) && get(heap) && get(info);
+    if (ok) { vox.resize(voxBytes); ok = get(vox); }
+    if (ok) ok = fgetc(f) == EOF;                            // trailing bytes: not a checkpoint of this geometry
     fclose(f);
-    return ok ? VH_OK : fail(VH_ERR_INVALID, "vh_load: short read");
+    if (!ok) return fail(VH_ERR_INVALID, "vh_load: short or oversized file (the context was not modified)");
+    const unsigned* hp = reinterpret_cast<const unsigned*>(heap.data());
+    for (int i = 0; i <= ctr.heapCounter; ++i)
+        if (hp[i] >= N) return fail(VH_ERR_INVALID, "vh_load: free list names a block id out of range (the context was not modified)");
+    // commit
+    VH_CUDA(cudaDeviceSynchronize());
+    Counters live;
+    VH_CUDA(cudaMemcpy(&live, c->v.ctr, sizeof(live), cudaMemcpyDeviceToHost));
+    ctr.icpSeq = live.icpSeq;                                // the exchange sequence stays with the running context
+    ctr.icpTicket = 0;
+    ctr.icpConverged = 0;
+    VH_CUDA(cudaMemcpy(c->v.entries, entries.data(), entries.size(), cudaMemcpyHostToDevice));
+    VH_CUDA(cudaMemcpy(c->v.chain, chain.data(), chain.size(), cudaMemcpyHostToDevice));
+    VH_CUDA(cudaMemcpy(c->v.heap, heap.data(), heap.size(), cudaMemcpyHostToDevice));
+    VH_CUDA(cudaMemcpy(c->v.blockInfo, info.data(), info.size(), cudaMemcpyHostToDevice));
+    VH_CUDA(cudaMemset(c->v.voxels, 0, N * 512 * sizeof(Voxel)));
+    if (voxBytes) VH_CUDA(cudaMemcpy(c->v.voxels + (size_t)first * 512, vox.data(), voxBytes, cudaMemcpyHostToDevice));
+    VH_CUDA(cudaMemcpy(c->v.ctr, &ctr, sizeof(ctr), cudaMemcpyHostToDevice));
+    return VH_OK;
 }
 int vh_extract_mesh(vh_context* c, float* d_tris, int capacity, int* h_count, vh_stream s) {
     if (!c || !h_count || capacity < 0 || (capacity > 0 && !d_tris)) return fail(VH_ERR_INVALID, "vh_extract_mesh: bad argument");
+    if (c->v.partCount > 1)      // cells on a block face need the neighbour block, which another rank may own
+        return fail(VH_ERR_UNSUPPORTED, "vh_extract_mesh: not defined on a partitioned context (no halo exchange); extract from the merged model");
     VH_CUDA(launch_extract_mesh(c, d_tris, capacity, &c->v.ctr->meshCount, S(s)));
     VH_CUDA(cudaMemcpyAsync(h_count, &c->v.ctr->meshCount, sizeof(int), cudaMemcpyDeviceToHost, S(s)));
     VH_CUDA(cudaStreamSynchronize(S(s)));

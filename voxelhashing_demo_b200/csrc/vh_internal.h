@@ -105,6 +105,8 @@ struct vh_context {
     vh::FrameParams* frame;
     vh::IcpState* icp;
     float* icpPartials;       // kIcpMaxBlocks x 32
+    unsigned long long* icpLL;   // persistent Align (k_track.cu): 2 x kIcpMaxBlocks x 32 {value, sequence} words
+    int icpCtas;              // CTAs of the persistent Align kernel (0 = one per SM); VH_ICP_CTAS / vh_set_tuning
     int* tileMin;             // raycast ray intervals, (W/8) x (H/8), float bit patterns
     int* tileMax;
     int numSMs;
@@ -134,6 +136,9 @@ cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, 
 cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                int row0, int row1, vh_icp_system* d_out, bool solve, bool first, bool chained, cudaStream_t s);
 cudaError_t launch_icp_solve(vh_context* c, const vh_icp_system* d_sys, cudaStream_t s);
+// whole Align in one persistent cooperative launch (k_track.cu); peers: fuse the cross-GPU all-reduce (vh_set_peers)
+cudaError_t launch_icp_align(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
+                             int row0, int row1, int iterations, bool peers, cudaStream_t s);
 cudaError_t launch_icp_iter_peer(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                  int row0, int row1, bool first, cudaStream_t s);
 cudaError_t launch_icp_reset(vh_context* c, bool resetDelta, cudaStream_t s);

@@ -70,12 +70,10 @@ cudaError_t enqueueIcp(vh_pipeline* p, int par, cudaStream_t s, int* n) {
     const int world = c->peers.world > 1 ? c->peers.world : 1, rank = world > 1 ? c->peers.rank : 0;
     const int base = c->v.H / world, rem = c->v.H % world;
     const int row0 = rank * base + (rank < rem ? rank : rem), row1 = row0 + base + (rank < rem ? 1 : 0);
-    for (int it = 0; it < p->iterations; ++it) {                           // CameraTracking.cpp:35
-        cudaError_t e = world > 1 ? launch_icp_iter_peer(c, p->verts[par], p->normals[par], tg, tgN, row0, row1, it == 0, s)
-                                  : launch_icp_iter_ex(c, p->verts[par], p->normals[par], tg, tgN, 0, c->v.H, nullptr, true, it == 0, it > 0, s);
-        if (e != cudaSuccess) return e;
-    }
-    *n = p->iterations;
+    // CameraTracking.cpp:35-67: the whole iteration loop is one persistent kernel (k_track.cu)
+    cudaError_t e = launch_icp_align(c, p->verts[par], p->normals[par], tg, tgN, row0, row1, p->iterations, world > 1, s);
+    if (e != cudaSuccess) return e;
+    *n = 1;
     return cudaSuccess;
 }
 cudaError_t enqueueFusion(vh_pipeline* p, int par, cudaStream_t s, int* n) {
@@ -132,6 +130,8 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
     if (!ctx || !out) return pfail(VH_ERR_INVALID, "vh_pipeline_create: null argument");
     if (mode == VH_TRACK_FRAME_TO_MODEL && ctx->cfg.policy != VH_POLICY_FIXED)
         return pfail(VH_ERR_INVALID, "vh_pipeline_create: frame-to-model tracking needs the Fixed policy");
+    if (mode == VH_TRACK_FRAME_TO_MODEL && ctx->v.partCount > 1)
+        return pfail(VH_ERR_UNSUPPORTED, "vh_pipeline_create: frame-to-model tracking raycasts the model, which a partitioned context holds only 1/P of");
     vh_pipeline* p = new vh_pipeline();
     memset(static_cast<void*>(p), 0, sizeof(*p));
     p->ctx = ctx;
@@ -223,7 +223,7 @@ static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, c
                 PCUDA(cudaGraphInstantiate(ex, *g, 0));
                 *have = true;
             } else {
-                *cnt = icp ? p->iterations : 3 + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
+                *cnt = icp ? 1 : 3 + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
             }
             PCUDA(cudaGraphLaunch(*ex, cs));
             return VH_OK;
@@ -251,7 +251,7 @@ static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, c
             PCUDA(cudaGraphInstantiate(&p->exec[par], g, 0));
             p->haveGraph[par] = true;
         } else {
-            n = p->iterations + 4 + (p->mode == VH_TRACK_FRAME_TO_MODEL ? 1 : 0) + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
+            n = 1 + 4 + (p->mode == VH_TRACK_FRAME_TO_MODEL ? 1 : 0) + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
         }
         PCUDA(cudaGraphLaunch(p->exec[par], st));
     } else {
