@@ -182,6 +182,11 @@ int vh_set_pose(vh_context* ctx, const float* pose_rowmajor, vh_stream s);
 /* Same, pose read from DEVICE memory at execution time (graph-capturable). */
 int vh_set_pose_device(vh_context* ctx, const float* d_pose_rowmajor, vh_stream s);
 int vh_alloc_blocks(vh_context* ctx, const float4* d_verts, const float4* d_normals, vh_stream s);
+/* The same allocation straight from the raw u16 depth image: the back-projection of
+ * vh_preprocess (ref CameraTrackingUtils.cu:50-76) runs in registers, same operations in the same order, so the
+ * requested blocks are identical; 2 B per pixel are read instead of the 16 B of the vertex map.  Not available with
+ * the bilateral front end (that allocates from the filtered vertex map). */
+int vh_alloc_blocks_depth(vh_context* ctx, const uint16_t* d_depth, vh_stream s);
 int vh_compact(vh_context* ctx, vh_stream s);             /* count stays on the device */
 int vh_integrate(vh_context* ctx, const float4* d_verts, vh_stream s);
 /* Fixed policy fast path: integrate from the dense metric depth image. */

@@ -58,7 +58,7 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_partitioned_fused_equals_single(built_library, tmp_path, world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -201,6 +201,37 @@ def test_fixed_sequence_bit_exact(built_library, oracle, dense):
     assert exact, f"Fixed sdf not bit-exact (worst {worst})"
 
 
+@pytest.mark.parametrize("policy", [POLICY_REF_EXACT, POLICY_FIXED])
+@pytest.mark.parametrize("size", ["vga", "ragged"])
+def test_alloc_from_raw_depth_equals_alloc_from_vertex_map(built_library, oracle, policy, size):
+    """k_alloc fed with the u16 depth image (2 B/px, back-projection in registers) requests exactly the
+    blocks it requests from the pre-processed vertex map (16 B/px) -- and both equal the oracle's table."""
+    kw = dict(policy=policy, numBuckets=100003, numVoxelBlocks=8192)
+    if policy == POLICY_FIXED:
+        kw.update(truncation=0.06, overflowSlots=4096)
+    cfg = Config(**kw) if size == "vga" else small_cfg(width=161, height=123, **kw)
+    pose = scenes.trajectory_C2(9).astype(np.float32)
+    depth = render(cfg, scenes.scene_S1(), pose)
+    depth[7:19, 30:90] = 0
+    depth[0, 0] = 65535
+    a, b = Context(cfg), Context(cfg)
+    v, n, df = gpu_preprocess(a, depth)
+    d16 = cu(depth.reshape(-1))
+    for _ in range(4 if policy == POLICY_REF_EXACT else 1):       # RefExact inserts one block per bucket per pass (Q4)
+        a.set_pose(pose)
+        a.alloc_blocks(v, n)
+        b.set_pose(pose)
+        b.alloc_blocks_depth(d16)
+    torch.cuda.synchronize()
+    sa, sb = entries_to_set(a.export_entries()), entries_to_set(b.export_entries())
+    assert sa == sb and len(sa) > 100
+    ot = oracle.OracleTable(cfg)
+    ov, _, _ = ot.preprocess(depth)
+    for _ in range(4 if policy == POLICY_REF_EXACT else 1):
+        ot.alloc(pose, ov)
+    assert sb == entries_to_set(ot.entries())
+
+
 def test_fixed_overflow_chain(built_library, oracle):
     """64 buckets x 2 slots force most blocks into the overflow arena; set equality must survive."""
     cfg = fixed_cfg(numBuckets=64, bucketSize=2, attachedLinkedListSize=64, overflowSlots=4096, numVoxelBlocks=4096,

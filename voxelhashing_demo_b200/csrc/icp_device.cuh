@@ -203,16 +203,17 @@ __device__ __forceinline__ IcpDev* devOf(IcpState* st) { return reinterpret_cast
 //     is accumulated in fp64 into the fp64 state D;
 //   * one Newton-Schulz step R <- 1.5 R - 0.5 R R^T R (fp64) re-orthonormalises the rotation, so the fp32
 //     rounding of exp(update) cannot accumulate over the thousands of updates of a long sequence.
-// dcol[k] = D[k][lane & 3] (the current fp64 delta).  Returns false when the iteration must stop (too few
-// correspondences / exactly-zero error, CameraTracking.cpp:55-58; singular system); otherwise lane L < 16 gets element
-// L of the new delta in pij.  sP: 16 doubles of shared memory private to the calling warp.
-__device__ __forceinline__ bool solveCoreWarp(const float* sys, const double (&dcol)[4], bool fixedPolicy, double* sP, double& pij) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+// The pieces, each executed by one converged warp with every lane computing the same values:
+//   solveTwistWarp   [JtJ | -Jtr] -> twist (v, omega); false when the iteration must stop (too few correspondences /
+//                    exactly-zero error, CameraTracking.cpp:55-58; singular system)
+//   expElementWarp   element (lane >> 2 & 3, lane & 3) of exp(twist^), fp32
+//   updateFp64Warp   D <- exp * D in fp64 + one Newton-Schulz step (per-launch path; dcol[k] = D[k][lane & 3])
+//   updateFp32Warp   delta <- exp * delta in fp32 (persistent Align: the delta is re-orthonormalised once, at the end)
+__device__ __forceinline__ bool solveTwistWarp(const float* sys, bool fixedPolicy, float (&tw)[6]) {
     if (fixedPolicy ? !(sys[28] >= 6.0f) : (sys[27] == 0.0f)) return false;     // CameraTracking.cpp:55-58
     // Gauss-Jordan on [JtJ | -Jtr], fp32, the WHOLE 6x7 system in the registers of every lane (uniform control
     // flow: no shuffles, no divergence; r1c probe: the row-per-lane shuffle form spent 3400 cycles here).
-    // The critical path is six dependent reciprocals; everything else is independent FMUL/FADD.
+    // The critical path is six dependent reciprocals; everything else is independent FMUL / FFMA.
     float M[6][7];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -226,23 +227,26 @@ __device__ __forceinline__ bool solveCoreWarp(const float* sys, const double (&d
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        const float inv = 1.0f / M[k][k];
+        const float inv = __frcp_rn(M[k][k]);                                    // == 1.0f / pivot, correctly rounded
 #pragma unroll
         for (int c = k + 1; c < 7; ++c) M[k][c] *= inv;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
             if (r == k) continue;
-            const float f = M[r][k];
+            const float f = -M[r][k];
 #pragma unroll
-            for (int c = k + 1; c < 7; ++c) M[r][c] -= f * M[k][c];
+            for (int c = k + 1; c < 7; ++c) M[r][c] = fmaf(f, M[k][c], M[r][c]);     // one rounding per update (the file is -fmad=false)
         }
     }
-    float tw[6];
     bool ok = true;
 #pragma unroll
     for (int c = 0; c < 6; ++c) { tw[c] = M[c][6]; ok = ok && isfinite(tw[c]); }
-    if (!ok) return false;                                                      // uniform: every lane holds the same values
-    // exp([[w]x v; 0 0]) element (i, j), fp32 (ref SE3Exp, twist = (v, omega)); every lane, same A, B, C
+    return ok;                                                                  // uniform: every lane holds the same values
+}
+
+// exp([[w]x v; 0 0]) element (i, j) = (lane >> 2 & 3, lane & 3), fp32 (ref SE3Exp, twist = (v, omega))
+__device__ __forceinline__ float expElementWarp(const float (&tw)[6]) {
+    const int lane = threadIdx.x & 31;
     const float t2 = tw[3] * tw[3] + tw[4] * tw[4] + tw[5] * tw[5];
     float A, B, C;
     if (t2 < 2.5e-3f) {
@@ -255,32 +259,40 @@ __device__ __forceinline__ bool solveCoreWarp(const float* sys, const double (&d
         sincosf(th, &sn, &cs);
         A = sn / th; B = (1.0f - cs) / t2; C = (th - sn) / (t2 * th);
     }
-    const int i = (lane >> 2) & 3, j = lane & 3;
-    float uij;
-    {
-        const float K[9] = {0.f, -tw[5], tw[4], tw[5], 0.f, -tw[3], -tw[4], tw[3], 0.f};
-        const int ii = i < 3 ? i : 0;
-        float K2row[3];
+    // Every lane builds the whole top 3x4 block (statically indexed: registers, no local memory) and keeps its element.
+    // K = [w]x, K^2 = w w^T - |w|^2 I;  R = I + A K + B K^2;  t = (I + B K + C K^2) v
+    const float wx = tw[3], wy = tw[4], wz = tw[5];
+    const float K[3][3] = {{0.f, -wz, wy}, {wz, 0.f, -wx}, {-wy, wx, 0.f}};
+    const float w[3] = {wx, wy, wz};
+    float E[3][4];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) K2row[c] = K[ii * 3] * K[c] + K[ii * 3 + 1] * K[3 + c] + K[ii * 3 + 2] * K[6 + c];
-        float rot = 0.f, tr = 0.f;
+    for (int r = 0; r < 3; ++r) {
+        float t = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float I = ii == c ? 1.0f : 0.0f;
-            if (c == j) rot = I + A * K[ii * 3 + c] + B * K2row[c];
-            tr += (I + B * K[ii * 3 + c] + C * K2row[c]) * tw[c];
+            const float I = r == c ? 1.0f : 0.0f;
+            const float k2 = r == c ? w[r] * w[c] - t2 : w[r] * w[c];
+            E[r][c] = I + A * K[r][c] + B * k2;
+            t += (I + B * K[r][c] + C * k2) * tw[c];
         }
-        uij = i == 3 ? (j == 3 ? 1.0f : 0.0f) : (j < 3 ? rot : tr);
+        E[r][3] = t;
     }
-    pij = 0.0;
+    const int i = (lane >> 2) & 3, j = lane & 3;
+    float e = j == 3 ? 1.0f : 0.0f;                          // row 3
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float uik = __shfl_sync(full, uij, i * 4 + k);
-        pij += (double)uik * dcol[k];
-    }
-    if (lane < 16) sP[lane] = pij;
-    __syncwarp();
-    if (lane < 16 && i < 3 && j < 3) {                                          // Newton-Schulz on the rotation block
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (i == r && j == c) e = E[r][c];
+    return e;
+}
+
+// One Newton-Schulz step R <- 1.5 R - 0.5 R R^T R on the rotation block of the 4x4 in sP (fp64, 16 doubles of shared
+// memory private to the warp, already written by lanes < 16); returns the lane's element.
+__device__ __forceinline__ double newtonSchulzWarp(const double* sP, double pij) {
+    const int lane = threadIdx.x & 31;
+    const int i = (lane >> 2) & 3, j = lane & 3;
+    if (lane < 16 && i < 3 && j < 3) {
         double rm = 0.0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -289,7 +301,39 @@ __device__ __forceinline__ bool solveCoreWarp(const float* sys, const double (&d
         }
         pij = 1.5 * pij - 0.5 * rm;
     }
+    return pij;
+}
+
+__device__ __forceinline__ double updateFp64Warp(float uij, const double (&dcol)[4], double* sP) {
+    const int lane = threadIdx.x & 31;
+    const int i = (lane >> 2) & 3;
+    double pij = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float uik = __shfl_sync(0xffffffffu, uij, i * 4 + k);
+        pij += (double)uik * dcol[k];
+    }
+    if (lane < 16) sP[lane] = pij;
     __syncwarp();
+    pij = newtonSchulzWarp(sP, pij);
+    __syncwarp();
+    return pij;
+}
+
+// delta <- exp * delta, fp32, two independent fused chains; dcol[k] = delta[k][lane & 3]
+__device__ __forceinline__ float updateFp32Warp(float uij, const float (&dcol)[4]) {
+    const int lane = threadIdx.x & 31;
+    const int i = (lane >> 2) & 3;
+    const float u0 = __shfl_sync(0xffffffffu, uij, i * 4 + 0), u1 = __shfl_sync(0xffffffffu, uij, i * 4 + 1);
+    const float u2 = __shfl_sync(0xffffffffu, uij, i * 4 + 2), u3 = __shfl_sync(0xffffffffu, uij, i * 4 + 3);
+    return fmaf(u0, dcol[0], u1 * dcol[1]) + fmaf(u2, dcol[2], u3 * dcol[3]);
+}
+
+// Per-launch path: dcol[k] = D[k][lane & 3] (the current fp64 delta); lane L < 16 gets element L of the new one.
+__device__ __forceinline__ bool solveCoreWarp(const float* sys, const double (&dcol)[4], bool fixedPolicy, double* sP, double& pij) {
+    float tw[6];
+    if (!solveTwistWarp(sys, fixedPolicy, tw)) return false;
+    pij = updateFp64Warp(expElementWarp(tw), dcol, sP);
     return true;
 }
 

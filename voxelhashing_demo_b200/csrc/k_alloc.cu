@@ -174,8 +174,16 @@ __device__ __forceinline__ void warpRequest(const View& v, const float* pose, un
     }
 }
 
-template <class P>
-__global__ void __launch_bounds__(256) k_alloc(View v, const float4* __restrict__ verts) {
+// Where the pixel's camera-space point comes from (pre-processing fused into its consumers):
+//   SRC_VERTS   the float4 vertex map (the reference's interface, allocBlocks(verts, normals)): 16 B per pixel
+//   SRC_DEPTH16 the raw u16 depth image, back-projected in registers with the operations of k_preprocess in the same
+//               order (metricDepth, K^-1 (x, y, 1), scale): 2 B per pixel, bit-identical points
+//   SRC_DEPTHF  the dense metric depth k_preprocess leaves behind for the integration (valid as a source when the last
+//               row of K^-1 is (0, 0, 1), so that depthf == the metric depth bit for bit): 4 B per pixel
+enum { SRC_VERTS = 0, SRC_DEPTH16 = 1, SRC_DEPTHF = 2 };
+
+template <class P, int SRC>
+__global__ void __launch_bounds__(256) k_alloc(View v, const void* __restrict__ src) {
     __shared__ unsigned long long filter[kFilterSize];
     __shared__ float sPose[16];
     for (int i = threadIdx.x; i < kFilterSize; i += 256) filter[i] = kFilterEmpty;
@@ -186,7 +194,19 @@ __global__ void __launch_bounds__(256) k_alloc(View v, const float4* __restrict_
     const int py = blockIdx.y * 8 + (threadIdx.x >> 5);
     const bool inside = px < v.W && py < v.H;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (inside) p = __ldg(verts + (size_t)py * v.W + px);
+    if (inside) {
+        const size_t idx = (size_t)py * v.W + px;
+        if (SRC == SRC_VERTS) p = __ldg(reinterpret_cast<const float4*>(src) + idx);
+        else {
+            float d;
+            if (SRC == SRC_DEPTH16) {
+                d = (float)__ldg(reinterpret_cast<const uint16_t*>(src) + idx) / v.depthScale;   // ref CameraTrackingUtils.cu:63-64
+                if (P::fixed && !(d > v.depthMin && d < v.depthMax)) d = 0.0f;
+            } else d = __ldg(reinterpret_cast<const float*>(src) + idx);
+            const float3 k = mul3(v.Kinv, (float)px, (float)py, 1.0f);                          // ref :69-70
+            p = make_float4(k.x * d, k.y * d, k.z * d, 1.0f);                                   // ref :72-73
+        }
+    }
 
     if (!P::fixed) {
         // ref :620-636: skip z == 0, transform by global_transform, one block per pixel (Q3)
@@ -304,11 +324,17 @@ cudaError_t launch_stream_in(vh_context* c, const VoxelEntry* entries, const Vox
     return cudaGetLastError();
 }
 
-cudaError_t launch_alloc(vh_context* c, const float4* verts, cudaStream_t s) {
+template <int SRC>
+static cudaError_t launchAllocFrom(vh_context* c, const void* src, cudaStream_t s) {
     dim3 grid((c->v.W + 31) / 32, (c->v.H + 7) / 8);
-    if (c->cfg.policy == VH_POLICY_FIXED) k_alloc<Fixed><<<grid, 256, 0, s>>>(c->v, verts);
-    else k_alloc<RefExact><<<grid, 256, 0, s>>>(c->v, verts);
+    if (c->cfg.policy == VH_POLICY_FIXED) k_alloc<Fixed, SRC><<<grid, 256, 0, s>>>(c->v, src);
+    else k_alloc<RefExact, SRC><<<grid, 256, 0, s>>>(c->v, src);
     return cudaGetLastError();
 }
+cudaError_t launch_alloc(vh_context* c, const float4* verts, cudaStream_t s) { return launchAllocFrom<SRC_VERTS>(c, verts, s); }
+cudaError_t launch_alloc_depth16(vh_context* c, const uint16_t* depth, cudaStream_t s) { return launchAllocFrom<SRC_DEPTH16>(c, depth, s); }
+// depthf == metric depth only when K^-1 maps (x, y, 1) to z = 1 exactly
+bool alloc_depthf_ok(const vh_context* c) { return c->v.Kinv[6] == 0.0f && c->v.Kinv[7] == 0.0f && c->v.Kinv[8] == 1.0f && c->v.bilatLut == nullptr; }
+cudaError_t launch_alloc_depthf(vh_context* c, const float* depthf, cudaStream_t s) { return launchAllocFrom<SRC_DEPTHF>(c, depthf, s); }
 
 }  // namespace vh

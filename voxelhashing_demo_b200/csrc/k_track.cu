@@ -22,11 +22,55 @@
 
 namespace vh {
 
-constexpr int kAlignBatch = 5;        // pixels in flight per thread (as k_icp_iter)
+#ifndef VH_ALIGN_BATCH
+#define VH_ALIGN_BATCH 3
+#endif
+constexpr int kAlignBatch = VH_ALIGN_BATCH;        // pixels in flight per thread (as k_icp_iter)
 
-// sequence-tagged row of the intra-GPU exchange: ll[slot][cta][32]
+#ifdef VH_ICP_TRACE
+// tools/align_trace.py: %globaltimer stamps [cta][iteration][slot]
+constexpr int kTraceIters = 24, kTraceSlots = 8;
+__device__ unsigned long long g_alignTrace[kIcpMaxBlocks * kTraceIters * kTraceSlots];
+__device__ __forceinline__ void atrace(int it, int slot) {
+    if (threadIdx.x == 0 && it < kTraceIters) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_alignTrace[((size_t)blockIdx.x * kTraceIters + it) * kTraceSlots + slot] = t;
+    }
+}
+#define VH_ATRACE(it, slot) atrace(it, slot)
+#else
+#define VH_ATRACE(it, slot)
+#endif
+
+// Sequence-tagged rows of the intra-GPU exchange.  Two levels, so that a CTA reads 16 + ceil(G/16) rows instead of G
+// (r2 trace of the one-level form, every CTA polling all 148 rows: 5.6 MB of L2 reads per poll round, 1.2-2.1 us from
+// the last CTA's publish to the sums being known everywhere):
+//   level 1: ll[slot][cta][32]                 -- every CTA's partial sums
+//   level 2: ll[2 x kIcpMaxBlocks x 32 + ...]  -- one row per group of kGroup CTAs, written by the group's first CTA
+constexpr int kGroup = kIcpThreads / 32;                       // 16: the leader reads its group's rows with one warp per row
+constexpr int kMaxGroups = (kIcpMaxBlocks + kGroup - 1) / kGroup;
 __device__ __forceinline__ unsigned long long* llRow(unsigned long long* ll, unsigned slot, unsigned cta) {
     return ll + ((size_t)slot * kIcpMaxBlocks + cta) * 32u;
+}
+__device__ __forceinline__ unsigned long long* llGroupRow(unsigned long long* ll, unsigned slot, unsigned group) {
+    return ll + (size_t)2 * kIcpMaxBlocks * 32u + ((size_t)slot * kMaxGroups + group) * 32u;
+}
+// sum of column `lane` of a 16 x 33 table in a fixed balanced order (depth 4)
+__device__ __forceinline__ float treeSum16(const float (*t)[33], int lane) {
+    float a[16];
+#pragma unroll
+    for (int g = 0; g < 16; ++g) a[g] = t[g][lane];
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+        for (int g = 0; g < w; ++g) a[g] = a[g] + a[g + w];
+    return a[0];
+}
+__device__ __forceinline__ float llPoll(const unsigned long long* p, unsigned seq) {
+    unsigned long long w = llLoadGpu(p);
+    while (!llReady(w, seq)) w = llLoadGpu(p);
+    return llValue(w);
 }
 
 template <class P>
@@ -35,26 +79,29 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
                                                               const float4* __restrict__ tg, const float4* __restrict__ tgN,
                                                               int row0, int row1, int iterations, PeerView pv) {
     __shared__ float sDelta[16];
-    __shared__ double sD[16];
     __shared__ double sP[16];
     __shared__ float sm[kIcpThreads / 32][32];
-    __shared__ double sRows[kIcpThreads / 32][33];
+    __shared__ float sRows[kIcpThreads / 32][33];
     __shared__ float sSys[32];
     __shared__ int sStop;
     constexpr int B = kAlignBatch;
-    constexpr int G = kIcpThreads / 32;                     // row groups of the exchange read: one warp per group
+    constexpr int G = kIcpThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int begin = row0 * v.W, end = row1 * v.W;
-    const int T = gridDim.x * blockDim.x;
+    // Balanced CONTIGUOUS pixel range per CTA (strided chunks gave the first few CTAs a whole extra pixel per thread --
+    // 5 instead of 4 at VGA -- and everybody waits for the slowest CTA in the exchange); contiguous also keeps the
+    // CTA's source pixels and its target gathers compact in L1.
+    const long long npx = (long long)(row1 - row0) * v.W;
+    const int lo = row0 * v.W + (int)(npx * blockIdx.x / gridDim.x);
+    const int hi = row0 * v.W + (int)(npx * (blockIdx.x + 1) / gridDim.x);
+    const unsigned nGroups = (gridDim.x + kGroup - 1) / kGroup;
+    const unsigned group = blockIdx.x / kGroup;
+    const bool leader = blockIdx.x % kGroup == 0;
     IcpDev* dev = devOf(st);
 
     // every CTA reads the sequence base before any CTA can finish (the base is only rewritten by CTA 0 after the last
     // exchange, which needs every CTA's contribution)
     const unsigned seq0 = __ldcg(&v.ctr->icpSeq);
-    if (threadIdx.x < 16) {
-        sDelta[threadIdx.x] = __ldcg(st->delta + threadIdx.x);
-        sD[threadIdx.x] = __ldcg(dev->D + threadIdx.x);
-    }
+    if (threadIdx.x < 16) sDelta[threadIdx.x] = __ldcg(st->delta + threadIdx.x);
     if (threadIdx.x == 0) sStop = 0;
     __syncthreads();
 
@@ -62,16 +109,17 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
     int solved = 0, exchanges = 0;
     for (int it = 0; it < iterations; ++it) {
         // ---- association + residual + Jacobian row + 29 running sums (as k_icp_iter) --------------------------
+        VH_ATRACE(it, 0);
         float acc[29];
 #pragma unroll
         for (int k = 0; k < 29; ++k) acc[k] = 0.f;
-        int i0 = begin + blockIdx.x * blockDim.x + threadIdx.x;
+        int i0 = lo + (int)threadIdx.x;
         float4 s[B];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int idx = i0 + j * T;
+            const int idx = i0 + j * kIcpThreads;
             s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < end) s[j] = __ldg(in + idx);
+            if (idx < hi) s[j] = __ldg(in + idx);
         }
         while (true) {
             Cand c[B];
@@ -84,17 +132,17 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
                 if (c[j].tidx >= 0) {
                     q[j] = __ldg(tg + c[j].tidx);
                     n[j] = __ldg(tgN + c[j].tidx);
-                    if (haveM) m[j] = __ldg(inN + i0 + j * T);
+                    if (haveM) m[j] = __ldg(inN + i0 + j * kIcpThreads);
                 }
             }
-            i0 += B * T;
-            const bool more = i0 < end;
+            i0 += B * kIcpThreads;
+            const bool more = i0 - (int)threadIdx.x < hi;    // CTA-uniform
             if (more) {
 #pragma unroll
                 for (int j = 0; j < B; ++j) {
-                    const int idx = i0 + j * T;
+                    const int idx = i0 + j * kIcpThreads;
                     s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < end) s[j] = __ldg(in + idx);
+                    if (idx < hi) s[j] = __ldg(in + idx);
                 }
             }
 #pragma unroll
@@ -105,60 +153,69 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
             }
             if (!more) break;
         }
+        VH_ATRACE(it, 1);
         const float tot = blockReduce29(acc, sm);           // warp 0, lane k < 29: this CTA's sum k
+        VH_ATRACE(it, 2);
 
-        // ---- exchange = grid barrier: publish my row, read everybody's ---------------------------------------
+        // ---- exchange = grid barrier, two levels -------------------------------------------------------------
         const unsigned seq = seq0 + (unsigned)it + 1u;
         const unsigned slot = seq & 1u;
         if (warp == 0) llStoreGpu(llRow(ll, slot, blockIdx.x) + lane, lane < 29 ? tot : 0.f, seq);
+        // Sums of <= 16 rows in a FIXED balanced order (identical in every CTA -> bit-identical delta everywhere), fp32:
+        // the rows are fp32 sums of ~2000 pixels each and a dependent fp64 add costs ~35 cycles here -- two chains of
+        // 16 were 0.55 us of the critical path of every iteration.
+        if (leader) {                                        // CTA-uniform: one warp per row of my group
+            const unsigned row = blockIdx.x + (unsigned)warp;
+            sRows[warp][lane] = row < gridDim.x ? llPoll(llRow(ll, slot, row) + lane, seq) : 0.f;
+            __syncthreads();
+            if (warp == 0) llStoreGpu(llGroupRow(ll, slot, group) + lane, treeSum16(sRows, lane), seq);
+            __syncthreads();
+        }
         {
-            // warp w reads rows w, w + G, ...; all first-round loads of a thread are in flight together
-            const int rows = ((int)gridDim.x - warp + G - 1) / G;       // rows this warp owns
-            double a = 0.0;
-            for (int r0 = 0; r0 < rows; r0 += 8) {
-                unsigned long long w[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (r0 + k < rows) w[k] = llLoadGpu(llRow(ll, slot, (unsigned)(warp + (r0 + k) * G)) + lane);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (r0 + k < rows) {
-                        while (!llReady(w[k], seq)) w[k] = llLoadGpu(llRow(ll, slot, (unsigned)(warp + (r0 + k) * G)) + lane);
-                        a += (double)llValue(w[k]);
-                    }
-                }
-            }
+            float a = 0.f;
+            for (unsigned g = (unsigned)warp; g < nGroups; g += G) a += llPoll(llGroupRow(ll, slot, g) + lane, seq);
             sRows[warp][lane] = a;
         }
         __syncthreads();
+        VH_ATRACE(it, 3);
         ++exchanges;
         if (warp == 0) {
-            double t = 0.0;
-#pragma unroll
-            for (int g = 0; g < G; ++g) t += sRows[g][lane];
-            float f = (float)t;
+            float f = treeSum16(sRows, lane);
             if (pv.world > 1) {                              // the cross-GPU collective, still inside the kernel
                 if (blockIdx.x == 0) peerScatter(pv, f, seq);
                 f = peerGather(pv, seq);
             }
             sSys[lane] = f;
             __syncwarp();
-            double dcol[4];
+            float dcol[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dcol[k] = sD[k * 4 + (lane & 3)];
-            double pij;
-            const bool ok = solveCoreWarp(sSys, dcol, P::fixed, sP, pij);
+            for (int k = 0; k < 4; ++k) dcol[k] = sDelta[k * 4 + (lane & 3)];
+            VH_ATRACE(it, 5);
+            float tw[6];
+            const bool ok = solveTwistWarp(sSys, P::fixed, tw);
             if (ok) {
-                if (lane < 16) { sD[lane] = pij; sDelta[lane] = (float)pij; }
+                const float d = updateFp32Warp(expElementWarp(tw), dcol);
+                __syncwarp();
+                if (lane < 16) sDelta[lane] = d;
             } else if (lane == 0) sStop = 1;
+            VH_ATRACE(it, 6);
         }
         __syncthreads();
+        VH_ATRACE(it, 4);
         if (sStop) break;                                    // uniform over the grid (and over the ranks): same sums everywhere
         ++solved;
     }
 
-    if (blockIdx.x == 0 && warp == 0) {                      // publish the result; every CTA holds the same one
-        if (lane < 16) { st->delta[lane] = sDelta[lane]; dev->D[lane] = sD[lane]; }
+    // Publish the result (every CTA holds the same one).  The fp32 products of the loop are re-orthonormalised ONCE,
+    // in fp64 (one Newton-Schulz step), so rounding cannot accumulate over the thousands of Aligns of a long
+    // sequence (the delta is the warm start of the next frame); the fp64 copy is what SE3Log / the per-launch solve read.
+    if (blockIdx.x == 0 && warp == 0) {
+        double pij = lane < 16 ? (double)sDelta[lane] : 0.0;
+        if (lane < 16) sP[lane] = pij;
+        __syncwarp();
+        if (solved > 0) pij = newtonSchulzWarp(sP, pij);
+        else if (lane < 16) pij = __ldcg(dev->D + lane);     // nothing solved: the state stays bit for bit as it was
+        if (lane < 16) { dev->D[lane] = pij; st->delta[lane] = (float)pij; }
         if (exchanges > 0) st->system[lane] = sSys[lane];
         if (lane == 0) {
             st->iterations += solved;
@@ -167,6 +224,12 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
         }
     }
 }
+
+#ifdef VH_ICP_TRACE
+extern "C" int vh_align_trace_read(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_alignTrace, sizeof(unsigned long long) * n);
+}
+#endif
 
 cudaError_t launch_icp_align(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN, int row0,
                              int row1, int iterations, bool peers, cudaStream_t s) {

@@ -174,8 +174,8 @@ int vh_create(const vh_config* cfg, vh_context** out) {
         c->icp = static_cast<IcpState*>(p);
     }
     chk(devAlloc(c, &c->icpPartials, (size_t)kIcpMaxBlocks * 32));
-    chk(devAlloc(c, &c->icpLL, (size_t)2 * kIcpMaxBlocks * 32));
-    if (e == cudaSuccess) chk(cudaMemset(c->icpLL, 0, sizeof(unsigned long long) * 2 * kIcpMaxBlocks * 32));   // sequence 0 = never written
+    chk(devAlloc(c, &c->icpLL, kIcpLLWords));
+    if (e == cudaSuccess) chk(cudaMemset(c->icpLL, 0, sizeof(unsigned long long) * kIcpLLWords));   // sequence 0 = never written
     if (const char* env = getenv("VH_ICP_CTAS")) c->icpCtas = atoi(env);
     {
         const size_t tiles = (size_t)((cfg->width + 7) / 8) * ((cfg->height + 7) / 8);
@@ -256,6 +256,15 @@ int vh_alloc_blocks(vh_context* c, const float4* d_verts, const float4* /*d_norm
     if (!c || !d_verts) return fail(VH_ERR_INVALID, "vh_alloc_blocks: null argument");
     if (c->cfg.policy == VH_POLICY_REF_EXACT) VH_CUDA(launch_reset_mutex(c, S(s)));   // SDF_Hashtable.cpp:24
     VH_CUDA(launch_alloc(c, d_verts, S(s)));
+    return VH_OK;
+}
+// Allocation straight from the raw u16 depth image: the back-projection of vh_preprocess happens in registers
+// (same operations, same order => the same blocks), 2 B per pixel instead of the 16 B of the vertex map.
+int vh_alloc_blocks_depth(vh_context* c, const uint16_t* d_depth, vh_stream s) {
+    if (!c || !d_depth) return fail(VH_ERR_INVALID, "vh_alloc_blocks_depth: null argument");
+    if (c->v.bilatLut != nullptr) return fail(VH_ERR_UNSUPPORTED, "vh_alloc_blocks_depth: the bilateral front end allocates from the filtered vertex map");
+    if (c->cfg.policy == VH_POLICY_REF_EXACT) VH_CUDA(launch_reset_mutex(c, S(s)));   // SDF_Hashtable.cpp:24
+    VH_CUDA(launch_alloc_depth16(c, d_depth, S(s)));
     return VH_OK;
 }
 int vh_compact(vh_context* c, vh_stream s) {

@@ -85,6 +85,8 @@ struct View {
 };
 
 constexpr int kIcpMaxBlocks = 1024;
+// exchange rows of the persistent Align kernel (k_track.cu): 2 parities x (one row per CTA + one row per group of 16 CTAs) x 32 words
+constexpr size_t kIcpLLWords = (size_t)2 * kIcpMaxBlocks * 32 + (size_t)2 * (kIcpMaxBlocks / 16) * 32;
 constexpr int kBilatLut = 1024;      // |delta depth| >= this many raw units contributes nothing
 
 // Fused all-reduce of the ICP normal equations over NVLink peer memory.
@@ -123,6 +125,9 @@ cudaError_t launch_reset(vh_context* c, cudaStream_t s);
 cudaError_t launch_set_frame_host(vh_context* c, const float* pose16, cudaStream_t s);
 cudaError_t launch_set_frame_device(vh_context* c, const float* d_pose, const float* d_delta, float* d_poseOut, cudaStream_t s);
 cudaError_t launch_alloc(vh_context* c, const float4* verts, cudaStream_t s);
+cudaError_t launch_alloc_depth16(vh_context* c, const uint16_t* depth, cudaStream_t s);   // back-projects in registers (2 B / pixel)
+cudaError_t launch_alloc_depthf(vh_context* c, const float* depthf, cudaStream_t s);      // from the dense metric depth (4 B / pixel)
+bool alloc_depthf_ok(const vh_context* c);
 cudaError_t launch_reset_mutex(vh_context* c, cudaStream_t s);
 cudaError_t launch_compact(vh_context* c, cudaStream_t s);
 cudaError_t launch_gc(vh_context* c, int scope, float sdfThreshold, float weightDecay, cudaStream_t s);

@@ -81,7 +81,8 @@ cudaError_t enqueueFusion(vh_pipeline* p, int par, cudaStream_t s, int* n) {
     cudaError_t e;
     int k = 0;
     if (c->cfg.policy == VH_POLICY_REF_EXACT) { e = launch_reset_mutex(c, s); if (e != cudaSuccess) return e; ++k; }
-    e = launch_alloc(c, p->verts[par], s);                                 // SDF_Hashtable.cpp:27
+    // SDF_Hashtable.cpp:27 -- from the 4 B / pixel metric depth when it determines the vertex exactly, else the vertex map
+    e = alloc_depthf_ok(c) ? launch_alloc_depthf(c, p->depthf[par], s) : launch_alloc(c, p->verts[par], s);
     if (e != cudaSuccess) return e;
     e = launch_compact(c, s);                                              // :30
     if (e != cudaSuccess) return e;
@@ -107,7 +108,7 @@ cudaError_t enqueueBody(vh_pipeline* p, int par, bool track, cudaStream_t s, int
     if (e != cudaSuccess) return e;
     ++k;
     if (c->cfg.policy == VH_POLICY_REF_EXACT) { e = launch_reset_mutex(c, s); if (e != cudaSuccess) return e; ++k; }
-    e = launch_alloc(c, in, s);                                            // SDF_Hashtable.cpp:27
+    e = alloc_depthf_ok(c) ? launch_alloc_depthf(c, p->depthf[par], s) : launch_alloc(c, in, s);   // SDF_Hashtable.cpp:27
     if (e != cudaSuccess) return e;
     e = launch_compact(c, s);                                              // :30
     if (e != cudaSuccess) return e;

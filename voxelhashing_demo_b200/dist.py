@@ -87,6 +87,9 @@ class PartitionedTracker:
         epilogue over NVLink instead of as a separate NCCL launch per iteration.  Falls back to NCCL if the
         symmetric-memory rendezvous is unavailable."""
         torch, dist = self.torch, self.dist
+        import sys
+
+        ok, ptrs, why = 0, None, ""
         try:
             import torch.distributed._symmetric_memory as symm
 
@@ -95,16 +98,22 @@ class PartitionedTracker:
             self._xbuf.zero_()
             hdl = symm.rendezvous(self._xbuf, self.group if self.group is not None else dist.group.WORLD)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
-            torch.cuda.synchronize()
-            dist.barrier(group=self.group)
-            self.ctx.set_peers(self.rank, self.world, ptrs)
             self._xhdl = hdl
-            self.fused = True
+            ok = 1
         except Exception as e:  # noqa: BLE001
-            import sys
-
-            print(f"[rank {self.rank}] symmetric memory unavailable ({e}); ICP all-reduce through NCCL", file=sys.stderr)
-            self.fused = False
+            why = str(e)
+        # The decision is COLLECTIVE: a rank that fell back to NCCL while its peers spin inside the fused kernel waiting
+        # for its mailbox stores would hang the job, so every rank uses the fused exchange only if every rank can.
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self.fused = bool(int(flag.item()))
+        if self.fused:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)                   # every region is zeroed before anyone can store into it
+            self.ctx.set_peers(self.rank, self.world, ptrs)
+        else:
+            print(f"[rank {self.rank}] fused peer exchange unavailable on at least one rank"
+                  + (f" (here: {why})" if why else "") + "; ICP all-reduce through NCCL", file=sys.stderr)
 
     def flush(self):
         """Order the current stream behind the fusion of the latest pushed frame (no-op without overlap)."""

@@ -191,6 +191,10 @@ class Context:
     def alloc_blocks(self, verts, normals=None, stream=None):
         L.check(self.lib.vh_alloc_blocks(self._h, _ptr(verts), _ptr(normals), _stream(stream)), "vh_alloc_blocks")
 
+    def alloc_blocks_depth(self, depth_u16, stream=None):
+        """Allocation straight from the raw u16 depth image (2 B / pixel; same blocks as from the vertex map)."""
+        L.check(self.lib.vh_alloc_blocks_depth(self._h, _ptr(depth_u16), _stream(stream)), "vh_alloc_blocks_depth")
+
     def compact(self, stream=None):
         L.check(self.lib.vh_compact(self._h, _stream(stream)), "vh_compact")
 
