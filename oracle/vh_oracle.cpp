@@ -949,31 +949,36 @@ inline Corr associate(const vo_config& c, const float* input, const float* input
         r.ok = true; r.q = V3{q[0], q[1], q[2]}; r.n = V3{n[0], n[1], n[2]}; r.p = V3{p.x, p.y, p.z}; r.d = d; r.qw = q[3]; r.nw = n[3];
         return r;
     }
+    // Fixed (DESIGN.md section 4 "ICP"): every product-sum is a fused chain, innermost term first
     if (!(s[2] > 0.0f)) return r;
-    V4 p = mul4(delta, V4{s[0], s[1], s[2], 1.0f});
-    if (!(p.z > 0.0f)) return r;
+    V4 p;
+    p.x = fmaf(delta[0], s[0], fmaf(delta[1], s[1], fmaf(delta[2], s[2], delta[3])));
+    p.y = fmaf(delta[4], s[0], fmaf(delta[5], s[1], fmaf(delta[6], s[2], delta[7])));
+    p.z = fmaf(delta[8], s[0], fmaf(delta[9], s[1], fmaf(delta[10], s[2], delta[11])));
+    p.w = 1.0f;
+    if (!(p.z > 1e-6f)) return r;
     const float fx = c.K[0], fy = c.K[4], cx = c.K[2], cy = c.K[5];
-    float iz = 1.0f / p.z;
+    float iz = 1.0f / p.z;                                                      // correctly rounded
     float u = fmaf(p.x * iz, fx, cx), v = fmaf(p.y * iz, fy, cy);
     int ix = f2i_rn(u), iy = f2i_rn(v);                                         // nearest pixel, ties to even (as integrate)
     if ((unsigned)ix >= (unsigned)W || (unsigned)iy >= (unsigned)H) return r;
     const float* q = target + (size_t)(iy * W + ix) * 4;
     const float* n = targetNormals + (size_t)(iy * W + ix) * 4;
     if (!(q[2] > 0.0f)) return r;
-    float nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    float nn = fmaf(n[0], n[0], fmaf(n[1], n[1], n[2] * n[2]));
     if (!(nn > 0.0f)) return r;
     V3 diff{p.x - q[0], p.y - q[1], p.z - q[2]};
-    float e2 = diff.x * diff.x + diff.y * diff.y + diff.z * diff.z;
+    float e2 = fmaf(diff.x, diff.x, fmaf(diff.y, diff.y, diff.z * diff.z));
     float lim = 3.0f * c.icpDistThres;
     if (!(e2 < lim * lim)) return r;
-    float d = diff.x * n[0] + diff.y * n[1] + diff.z * n[2];
+    float d = fmaf(diff.x, n[0], fmaf(diff.y, n[1], diff.z * n[2]));
     if (!(fabsf(d) < c.icpDistThres)) return r;
     if (inputNormals && c.icpNormalThres > -1.0f) {
         const float* m = inputNormals + (size_t)idx * 4;
-        float rx = delta[0] * m[0] + delta[1] * m[1] + delta[2] * m[2];
-        float ry = delta[4] * m[0] + delta[5] * m[1] + delta[6] * m[2];
-        float rz = delta[8] * m[0] + delta[9] * m[1] + delta[10] * m[2];
-        float cosang = rx * n[0] + ry * n[1] + rz * n[2];
+        float rx = fmaf(delta[0], m[0], fmaf(delta[1], m[1], delta[2] * m[2]));
+        float ry = fmaf(delta[4], m[0], fmaf(delta[5], m[1], delta[6] * m[2]));
+        float rz = fmaf(delta[8], m[0], fmaf(delta[9], m[1], delta[10] * m[2]));
+        float cosang = fmaf(rx, n[0], fmaf(ry, n[1], rz * n[2]));
         if (!(cosang > c.icpNormalThres)) return r;
     }
     r.ok = true; r.q = V3{q[0], q[1], q[2]}; r.n = V3{n[0], n[1], n[2]}; r.p = V3{p.x, p.y, p.z}; r.d = d; r.qw = q[3]; r.nw = n[3];

@@ -13,6 +13,8 @@ os.environ["VH_EXTRA_NVCC_FLAGS"] = "-DVH_ICP_TRACE"
 for a in sys.argv[1:]:
     if a.startswith("ctas="):
         os.environ["VH_ICP_CTAS"] = a.split("=")[1]
+    if a.startswith("ablate="):
+        os.environ["VH_EXTRA_NVCC_FLAGS"] += " -DVH_ALIGN_ABLATE=" + a.split("=")[1]
     if a.startswith("batch="):
         os.environ["VH_EXTRA_NVCC_FLAGS"] += " -DVH_ALIGN_BATCH=" + a.split("=")[1]
 import torch  # noqa: E402

@@ -31,15 +31,28 @@ __device__ __forceinline__ Cand project(const View& v, const float* __restrict__
         c.tidx = iy * v.W + ix;
         return c;
     }
+    // Fixed: every product-sum is a fused chain (DESIGN.md section 4 "ICP"; the oracle mirrors it with fmaf): 9 FFMA
+    // for the transform instead of 9 FMUL + 9 FADD -- the loop is instruction-issue bound (r2 ncu: 210 SASS
+    // instructions per pixel, 64 % issue utilisation).
     if (!(s.z > 0.0f)) return c;
-    float4 p = mul4(delta, s.x, s.y, s.z, 1.0f);
-    if (!(p.z > 0.0f)) return c;
-    const float rz = __frcp_rn(p.z);                                            // == 1.0f / p.z, correctly rounded
-    const float u = fmaf(p.x * rz, v.fx, v.cx), w = fmaf(p.y * rz, v.fy, v.cy);
-    const int ix = __float2int_rn(u), iy = __float2int_rn(w);                  // nearest pixel, ties to even (as integrate)
-    if ((unsigned)ix >= (unsigned)v.W || (unsigned)iy >= (unsigned)v.H) return c;
-    c.p = make_float3(p.x, p.y, p.z);
-    c.tidx = iy * v.W + ix;
+    const float px = fmaf(delta[0], s.x, fmaf(delta[1], s.y, fmaf(delta[2], s.z, delta[3])));
+    const float py = fmaf(delta[4], s.x, fmaf(delta[5], s.y, fmaf(delta[6], s.z, delta[7])));
+    const float pz = fmaf(delta[8], s.x, fmaf(delta[9], s.y, fmaf(delta[10], s.z, delta[11])));
+    if (!(pz > 1e-6f)) return c;
+    // 1 / pz correctly rounded: MUFU.RCP + one Newton step, the in-range path of __frcp_rn without its exponent-window
+    // branch (pz is in (1e-6, ~depthMax + |t|) here)
+    float rz;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rz) : "f"(pz));
+    rz = fmaf(rz, fmaf(-pz, rz, 1.0f), rz);
+    const float u = fmaf(px * rz, v.fx, v.cx), w = fmaf(py * rz, v.fy, v.cy);
+    // nearest pixel, ties to even, without F2I (quarter-rate pipe): u + 1.5 * 2^23 leaves the rounded value in the low
+    // mantissa bits -- identical to __float2int_rn for |u| < 2^22; anything else (inf, NaN included) lands outside
+    // [0, W) as an unsigned number and is rejected by the range check (as in k_integrate.cu)
+    const unsigned ix = (unsigned)(__float_as_int(u + 12582912.0f) - 0x4B400000);
+    const unsigned iy = (unsigned)(__float_as_int(w + 12582912.0f) - 0x4B400000);
+    if (ix >= (unsigned)v.W || iy >= (unsigned)v.H) return c;
+    c.p = make_float3(px, py, pz);
+    c.tidx = (int)(iy * (unsigned)v.W + ix);
     return c;
 }
 
@@ -50,22 +63,24 @@ __device__ __forceinline__ Corr accept(const View& v, const float* __restrict__ 
     Corr r;
     r.ok = false;
     const float dx = c.p.x - q.x, dy = c.p.y - q.y, dz = c.p.z - q.z;           // ref :168
-    const float d = dx * n.x + dy * n.y + dz * n.z;                             // ref :169
+    float d;
     if (!P::fixed) {
+        d = dx * n.x + dy * n.y + dz * n.z;                                     // ref :169
         if (!(d < v.icpDistThres)) return r;                                    // ref :170 (signed, Q21)
     } else {
         if (!(q.z > 0.0f)) return r;
-        float nn = n.x * n.x + n.y * n.y + n.z * n.z;
+        const float nn = fmaf(n.x, n.x, fmaf(n.y, n.y, n.z * n.z));
         if (!(nn > 0.0f)) return r;
-        float e2 = dx * dx + dy * dy + dz * dz;
-        float lim = 3.0f * v.icpDistThres;
+        const float e2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        const float lim = 3.0f * v.icpDistThres;
         if (!(e2 < lim * lim)) return r;
+        d = fmaf(dx, n.x, fmaf(dy, n.y, dz * n.z));
         if (!(fabsf(d) < v.icpDistThres)) return r;
         if (haveM) {
-            float rx = delta[0] * m.x + delta[1] * m.y + delta[2] * m.z;
-            float ry = delta[4] * m.x + delta[5] * m.y + delta[6] * m.z;
-            float rz = delta[8] * m.x + delta[9] * m.y + delta[10] * m.z;
-            float cosang = rx * n.x + ry * n.y + rz * n.z;
+            const float rx = fmaf(delta[0], m.x, fmaf(delta[1], m.y, delta[2] * m.z));
+            const float ry = fmaf(delta[4], m.x, fmaf(delta[5], m.y, delta[6] * m.z));
+            const float rz = fmaf(delta[8], m.x, fmaf(delta[9], m.y, delta[10] * m.z));
+            const float cosang = fmaf(rx, n.x, fmaf(ry, n.y, rz * n.z));
             if (!(cosang > v.icpNormalThres)) return r;
         }
     }
@@ -211,36 +226,42 @@ __device__ __forceinline__ IcpDev* devOf(IcpState* st) { return reinterpret_cast
 //   updateFp32Warp   delta <- exp * delta in fp32 (persistent Align: the delta is re-orthonormalised once, at the end)
 __device__ __forceinline__ bool solveTwistWarp(const float* sys, bool fixedPolicy, float (&tw)[6]) {
     if (fixedPolicy ? !(sys[28] >= 6.0f) : (sys[27] == 0.0f)) return false;     // CameraTracking.cpp:55-58
-    // Gauss-Jordan on [JtJ | -Jtr], fp32, the WHOLE 6x7 system in the registers of every lane (uniform control
-    // flow: no shuffles, no divergence; r1c probe: the row-per-lane shuffle form spent 3400 cycles here).
-    // The critical path is six dependent reciprocals; everything else is independent FMUL / FFMA.
-    float M[6][7];
+    // Symmetric Gaussian elimination (LDL^T, right-looking) on the LOWER triangle of [JtJ | -Jtr], fp32, the whole system
+    // in the registers of every lane (uniform control flow: no shuffles, no divergence; r1c probe: a row-per-lane
+    // shuffle form spent 3400 cycles here).  JtJ is SPD when the scene constrains all six degrees of freedom, so no
+    // row exchanges are needed (as stable as Cholesky); otherwise a pivot is ~0, the result is not finite and the
+    // iteration stops.  Half the multiply-adds of the Gauss-Jordan form r1 used (r2 ncu: the single warp running the
+    // solve is a chain of dependent fp32 operations at ~0.25 IPC while 15 warps wait at the barrier; the critical path
+    // is six dependent reciprocals, so fewer instructions = shorter wait).
+    float A[6][6], bb[6], inv[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
-        for (int j = i; j < 6; ++j) {
-            const float a = sys[i * 6 - (i * (i - 1)) / 2 + (j - i)];          // selfadjointView, Solver.cpp:92
-            M[i][j] = a;
-            M[j][i] = a;
-        }
-        M[i][6] = -sys[21 + i];                                                // update = -(JTJinv * JTr), :110
+        for (int j = i; j < 6; ++j) A[j][i] = sys[i * 6 - (i * (i - 1)) / 2 + (j - i)];   // selfadjointView, Solver.cpp:92
+        bb[i] = -sys[21 + i];                                                  // update = -(JTJinv * JTr), :110
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        const float inv = __frcp_rn(M[k][k]);                                    // == 1.0f / pivot, correctly rounded
+        inv[k] = __frcp_rn(A[k][k]);                                            // == 1.0f / pivot, correctly rounded
 #pragma unroll
-        for (int c = k + 1; c < 7; ++c) M[k][c] *= inv;
+        for (int i = k + 1; i < 6; ++i) {
+            const float l = -(A[i][k] * inv[k]);
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            if (r == k) continue;
-            const float f = -M[r][k];
-#pragma unroll
-            for (int c = k + 1; c < 7; ++c) M[r][c] = fmaf(f, M[k][c], M[r][c]);     // one rounding per update (the file is -fmad=false)
+            for (int j = k + 1; j <= i; ++j) A[i][j] = fmaf(l, A[j][k], A[i][j]);   // one rounding per update (the file is -fmad=false)
+            bb[i] = fmaf(l, bb[k], bb[i]);
         }
+    }
+    tw[5] = bb[5] * inv[5];
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+        float t = bb[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) t = fmaf(-A[j][i], tw[j], t);
+        tw[i] = t * inv[i];
     }
     bool ok = true;
 #pragma unroll
-    for (int c = 0; c < 6; ++c) { tw[c] = M[c][6]; ok = ok && isfinite(tw[c]); }
+    for (int c = 0; c < 6; ++c) ok = ok && isfinite(tw[c]);
     return ok;                                                                  // uniform: every lane holds the same values
 }
 

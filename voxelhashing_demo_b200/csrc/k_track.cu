@@ -22,6 +22,9 @@
 
 namespace vh {
 
+#ifndef VH_ALIGN_ABLATE
+#define VH_ALIGN_ABLATE 0
+#endif
 #ifndef VH_ALIGN_BATCH
 #define VH_ALIGN_BATCH 3
 #endif
@@ -77,7 +80,7 @@ template <class P>
 __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* st, unsigned long long* ll,
                                                               const float4* __restrict__ in, const float4* __restrict__ inN,
                                                               const float4* __restrict__ tg, const float4* __restrict__ tgN,
-                                                              int row0, int row1, int iterations, PeerView pv) {
+                                                              int row0, int row1, int iterations, PeerView pv, const float* poseIn, float* poseOut) {
     __shared__ float sDelta[16];
     __shared__ double sP[16];
     __shared__ float sm[kIcpThreads / 32][32];
@@ -164,6 +167,11 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
         // Sums of <= 16 rows in a FIXED balanced order (identical in every CTA -> bit-identical delta everywhere), fp32:
         // the rows are fp32 sums of ~2000 pixels each and a dependent fp64 add costs ~35 cycles here -- two chains of
         // 16 were 0.55 us of the critical path of every iteration.
+#if VH_ALIGN_ABLATE == 2                                     // timing experiment: no exchange (own sums only)
+        sRows[warp][lane] = warp == 0 ? (lane < 29 ? tot : 0.f) : 0.f;
+        __syncthreads();
+        if (false)
+#endif
         if (leader) {                                        // CTA-uniform: one warp per row of my group
             const unsigned row = blockIdx.x + (unsigned)warp;
             sRows[warp][lane] = row < gridDim.x ? llPoll(llRow(ll, slot, row) + lane, seq) : 0.f;
@@ -171,12 +179,14 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
             if (warp == 0) llStoreGpu(llGroupRow(ll, slot, group) + lane, treeSum16(sRows, lane), seq);
             __syncthreads();
         }
+#if VH_ALIGN_ABLATE != 2
         {
             float a = 0.f;
             for (unsigned g = (unsigned)warp; g < nGroups; g += G) a += llPoll(llGroupRow(ll, slot, g) + lane, seq);
             sRows[warp][lane] = a;
         }
         __syncthreads();
+#endif
         VH_ATRACE(it, 3);
         ++exchanges;
         if (warp == 0) {
@@ -192,7 +202,13 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
             for (int k = 0; k < 4; ++k) dcol[k] = sDelta[k * 4 + (lane & 3)];
             VH_ATRACE(it, 5);
             float tw[6];
+#if VH_ALIGN_ABLATE == 1                                     // timing experiment: no solve (zero update)
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) tw[k] = sSys[k] * 1e-30f;
+#else
             const bool ok = solveTwistWarp(sSys, P::fixed, tw);
+#endif
             if (ok) {
                 const float d = updateFp32Warp(expElementWarp(tw), dcol);
                 __syncwarp();
@@ -217,6 +233,20 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
         else if (lane < 16) pij = __ldcg(dev->D + lane);     // nothing solved: the state stays bit for bit as it was
         if (lane < 16) { dev->D[lane] = pij; st->delta[lane] = (float)pij; }
         if (exchanges > 0) st->system[lane] = sSys[lane];
+        if (poseOut != nullptr) {
+            // camera -> world chain T_k = T_{k-1} * delta (what getTransform() feeds integrate with, Application.cpp:75-84):
+            // the same products in the same order as k_set_frame, so both routes give the same bits
+            __syncwarp();
+            if (lane < 16) sDelta[lane] = (float)pij;
+            __syncwarp();
+            if (lane < 16) {
+                const int r = lane >> 2, c = lane & 3;
+                const float t = poseIn[r * 4 + 0] * sDelta[0 * 4 + c] + poseIn[r * 4 + 1] * sDelta[1 * 4 + c] +
+                                poseIn[r * 4 + 2] * sDelta[2 * 4 + c] + poseIn[r * 4 + 3] * sDelta[3 * 4 + c];
+                __syncwarp(0x0000ffffu);                     // every lane has read the old pose (poseOut may alias poseIn)
+                poseOut[lane] = t;
+            }
+        }
         if (lane == 0) {
             st->iterations += solved;
             v.ctr->icpConverged = sStop;
@@ -232,7 +262,7 @@ extern "C" int vh_align_trace_read(unsigned long long* host, int n) {
 #endif
 
 cudaError_t launch_icp_align(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN, int row0,
-                             int row1, int iterations, bool peers, cudaStream_t s) {
+                             int row1, int iterations, bool peers, const float* d_poseIn, float* d_poseOut, cudaStream_t s) {
     if (iterations <= 0) return cudaSuccess;
     int g = ((row1 - row0) * c->v.W + kIcpThreads - 1) / kIcpThreads;
     int cap = c->icpCtas > 0 ? c->icpCtas : c->numSMs;
@@ -254,8 +284,8 @@ cudaError_t launch_icp_align(vh_context* c, const float4* in, const float4* inN,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (c->cfg.policy == VH_POLICY_FIXED)
-        return cudaLaunchKernelEx(&cfg, k_icp_align<Fixed>, c->v, c->icp, c->icpLL, in, inN, tg, tgN, row0, row1, iterations, pv);
-    return cudaLaunchKernelEx(&cfg, k_icp_align<RefExact>, c->v, c->icp, c->icpLL, in, inN, tg, tgN, row0, row1, iterations, pv);
+        return cudaLaunchKernelEx(&cfg, k_icp_align<Fixed>, c->v, c->icp, c->icpLL, in, inN, tg, tgN, row0, row1, iterations, pv, d_poseIn, d_poseOut);
+    return cudaLaunchKernelEx(&cfg, k_icp_align<RefExact>, c->v, c->icp, c->icpLL, in, inN, tg, tgN, row0, row1, iterations, pv, d_poseIn, d_poseOut);
 }
 
 }  // namespace vh

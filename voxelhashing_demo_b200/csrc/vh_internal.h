@@ -141,9 +141,10 @@ cudaError_t launch_icp_iter(vh_context* c, const float4* in, const float4* inN, 
 cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                int row0, int row1, vh_icp_system* d_out, bool solve, bool first, bool chained, cudaStream_t s);
 cudaError_t launch_icp_solve(vh_context* c, const vh_icp_system* d_sys, cudaStream_t s);
-// whole Align in one persistent cooperative launch (k_track.cu); peers: fuse the cross-GPU all-reduce (vh_set_peers)
+// whole Align in one persistent cooperative launch (k_track.cu); peers: fuse the cross-GPU all-reduce (vh_set_peers);
+// d_poseOut (optional, may alias d_poseIn): 16 floats, row-major camera -> world, = d_poseIn * delta at the end of the launch
 cudaError_t launch_icp_align(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
-                             int row0, int row1, int iterations, bool peers, cudaStream_t s);
+                             int row0, int row1, int iterations, bool peers, const float* d_poseIn, float* d_poseOut, cudaStream_t s);
 cudaError_t launch_icp_iter_peer(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
                                  int row0, int row1, bool first, cudaStream_t s);
 cudaError_t launch_icp_reset(vh_context* c, bool resetDelta, cudaStream_t s);

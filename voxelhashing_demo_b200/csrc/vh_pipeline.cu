@@ -8,11 +8,14 @@
 // frame's maps are the ICP target).  The pose lives in device memory and is chained on the device,
 // so frame k+1 can be enqueued before frame k has finished.
 //
-// VH_PIPE_OVERLAP (frame-to-frame): two graphs per parity -- { ICP x iterations } on the caller's stream and
-// { alloc -> compact -> integrate } on an internal stream that starts once pose_k is published; the caller's
-// stream goes straight on to frame k+1 and only waits for fusion(k) before pose_{k+1} replaces the frame
-// constants.  On a partitioned context with peer mailboxes (vh_set_peers) the ICP graph reduces this rank's image
-// rows and carries the cross-GPU all-reduce in its kernels' epilogue.
+// VH_PIPE_OVERLAP (frame-to-frame):
+//   caller's stream:  preprocess(k) -> Align(k) [one persistent kernel; its tail also chains the pose, T_k = T_{k-1} * delta]
+//   fusion stream:    [wait Align(k)] -> frame constants(k) -> { alloc -> compact -> integrate } (a graph per parity)
+// The caller's stream never waits for a fusion (only for buffer reuse two frames later and for the 3-microsecond frame-
+// constants kernel that reads the pose the next Align will overwrite), so its critical path per frame is preprocess +
+// Align; the Align grid leaves a few SMs free (vh_context::icpCtas) and fusion(k) runs there beside Align(k+1).
+// On a partitioned context with peer mailboxes (vh_set_peers) the Align kernel reduces this rank's image rows and
+// carries the cross-GPU all-reduce inside.
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -28,7 +31,9 @@ struct vh_pipeline {
     bool useGraph;
     long long frame;
     long long launches;
-    float* d_pose;                 // camera -> world of the latest frame, row-major
+    float* d_poseBuf[2];           // camera -> world, row-major; the overlapped schedule ping-pongs so that Align(k+1) never
+    int poseIdx;                   // overwrites the pose the frame-constants kernel of frame k still has to read
+    float* d_pose;                 // = d_poseBuf[poseIdx]: pose of the latest frame
     uint16_t* d_depthStage[2];     // H2D landing buffers of push_host (double-buffered)
     cudaStream_t copyStream;       // H2D of frame k+1 overlaps the compute of frame k
     cudaEvent_t evCopied[2], evConsumed[2];
@@ -43,9 +48,11 @@ struct vh_pipeline {
     bool haveGraph[2];
     // overlapped schedule (VH_PIPE_OVERLAP): fusion of frame k runs on its own stream beside preprocess + ICP of frame k+1
     bool overlap;
-    cudaStream_t fuseStream;
-    cudaEvent_t evPose, evFused;
-    bool fusePending;              // evFused has been recorded and not yet waited for by the caller's stream
+    cudaStream_t fuseStream, trackStream;
+    cudaEvent_t evPre;
+    cudaEvent_t evAligned, evFused[2];
+    bool fusePending;              // a fusion has been enqueued since the last reset
+    int lastFusePar;
     cudaGraph_t fuseGraph[2];
     cudaGraphExec_t fuseExec[2];
     bool haveFuseGraph[2];
@@ -61,7 +68,7 @@ int pfail(int code, const char* what, cudaError_t e = cudaSuccess) {
 }
 #define PCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return pfail(VH_ERR_CUDA, #expr, _e); } while (0)
 
-cudaError_t enqueueIcp(vh_pipeline* p, int par, cudaStream_t s, int* n) {
+cudaError_t enqueueIcp(vh_pipeline* p, int par, const float* d_poseIn, float* d_poseOut, cudaStream_t s, int* n) {
     vh_context* c = p->ctx;
     const float4* tg = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelVerts : p->verts[1 - par];
     const float4* tgN = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelNormals : p->normals[1 - par];
@@ -71,7 +78,7 @@ cudaError_t enqueueIcp(vh_pipeline* p, int par, cudaStream_t s, int* n) {
     const int base = c->v.H / world, rem = c->v.H % world;
     const int row0 = rank * base + (rank < rem ? rank : rem), row1 = row0 + base + (rank < rem ? 1 : 0);
     // CameraTracking.cpp:35-67: the whole iteration loop is one persistent kernel (k_track.cu)
-    cudaError_t e = launch_icp_align(c, p->verts[par], p->normals[par], tg, tgN, row0, row1, p->iterations, world > 1, s);
+    cudaError_t e = launch_icp_align(c, p->verts[par], p->normals[par], tg, tgN, row0, row1, p->iterations, world > 1, d_poseIn, d_poseOut, s);
     if (e != cudaSuccess) return e;
     *n = 1;
     return cudaSuccess;
@@ -99,7 +106,7 @@ cudaError_t enqueueBody(vh_pipeline* p, int par, bool track, cudaStream_t s, int
     int k = 0;
     const float4* in = p->verts[par];
     if (track) {
-        e = enqueueIcp(p, par, s, &k);
+        e = enqueueIcp(p, par, nullptr, nullptr, s, &k);
         if (e != cudaSuccess) return e;
         e = launch_set_frame_device(c, p->d_pose, c->icp->delta, p->d_pose, s);   // T_k = T_{k-1} * delta
     } else {
@@ -144,7 +151,9 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
     const size_t px = (size_t)ctx->v.W * ctx->v.H;
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    chk(cudaMalloc((void**)&p->d_pose, 16 * sizeof(float)));
+    chk(cudaMalloc((void**)&p->d_poseBuf[0], 2 * 16 * sizeof(float)));
+    p->d_poseBuf[1] = p->d_poseBuf[0] ? p->d_poseBuf[0] + 16 : nullptr;
+    p->d_pose = p->d_poseBuf[0];
     chk(cudaStreamCreateWithFlags(&p->copyStream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         chk(cudaMalloc((void**)&p->verts[i], px * sizeof(float4)));
@@ -155,9 +164,18 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
         chk(cudaEventCreateWithFlags(&p->evConsumed[i], cudaEventDisableTiming));
     }
     if (p->overlap) {
-        chk(cudaStreamCreateWithFlags(&p->fuseStream, cudaStreamNonBlocking));
-        chk(cudaEventCreateWithFlags(&p->evPose, cudaEventDisableTiming));
-        chk(cudaEventCreateWithFlags(&p->evFused, cudaEventDisableTiming));
+        // Align runs on its own HIGH-priority stream: when Align(k) retires, Align(k+1) and the fusion of frame k become
+        // runnable together, and the block scheduler must give the SMs to the cooperative Align grid first -- the fusion
+        // kernels then fill the SMs the Align grid leaves free (a caller's stream cannot be given a lower priority than
+        // the default, so the tracking is raised instead)
+        int least = 0, greatest = 0;
+        chk(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        chk(cudaStreamCreateWithPriority(&p->trackStream, cudaStreamNonBlocking, greatest));
+        chk(cudaEventCreateWithFlags(&p->evPre, cudaEventDisableTiming));
+        chk(cudaStreamCreateWithPriority(&p->fuseStream, cudaStreamNonBlocking, least));
+        chk(cudaEventCreateWithFlags(&p->evAligned, cudaEventDisableTiming));
+        chk(cudaEventCreateWithFlags(&p->evFused[0], cudaEventDisableTiming));
+        chk(cudaEventCreateWithFlags(&p->evFused[1], cudaEventDisableTiming));
     }
     if (mode == VH_TRACK_FRAME_TO_MODEL) {
         chk(cudaMalloc((void**)&p->modelVerts, px * sizeof(float4)));
@@ -181,9 +199,12 @@ void vh_pipeline_destroy(vh_pipeline* p) {
     }
     if (p->copyStream) cudaStreamDestroy(p->copyStream);
     if (p->fuseStream) { cudaStreamSynchronize(p->fuseStream); cudaStreamDestroy(p->fuseStream); }
-    if (p->evPose) cudaEventDestroy(p->evPose);
-    if (p->evFused) cudaEventDestroy(p->evFused);
-    cudaFree(p->modelVerts); cudaFree(p->modelNormals); cudaFree(p->d_pose);
+    if (p->trackStream) { cudaStreamSynchronize(p->trackStream); cudaStreamDestroy(p->trackStream); }
+    if (p->evPre) cudaEventDestroy(p->evPre);
+    if (p->evAligned) cudaEventDestroy(p->evAligned);
+    if (p->evFused[0]) cudaEventDestroy(p->evFused[0]);
+    if (p->evFused[1]) cudaEventDestroy(p->evFused[1]);
+    cudaFree(p->modelVerts); cudaFree(p->modelNormals); cudaFree(p->d_poseBuf[0]);
     delete p;
 }
 
@@ -192,8 +213,11 @@ int vh_pipeline_reset(vh_pipeline* p, const float* pose16_host, vh_stream s) {
     if (!p) return pfail(VH_ERR_INVALID, "vh_pipeline_reset: null pipeline");
     const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+    if (p->trackStream) PCUDA(cudaStreamSynchronize(p->trackStream));
     if (p->fuseStream) PCUDA(cudaStreamSynchronize(p->fuseStream));
     p->fusePending = false;
+    p->poseIdx = 0;
+    p->d_pose = p->d_poseBuf[0];
     PCUDA(cudaStreamSynchronize(st));
     PCUDA(cudaMemcpy(p->d_pose, pose16_host ? pose16_host : ident, 16 * sizeof(float), cudaMemcpyHostToDevice));
     PCUDA(launch_icp_reset(p->ctx, true, st));
@@ -204,40 +228,44 @@ int vh_pipeline_reset(vh_pipeline* p, const float* pose16_host, vh_stream s) {
 static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, cudaEvent_t afterPreprocess) {
     vh_context* c = p->ctx;
     const int par = (int)(p->frame & 1);
+    // overlapped schedule: the maps of this parity were read by the fusion of frame k-2 on the other stream
+    if (p->overlap && st != nullptr && p->frame >= 2) PCUDA(cudaStreamWaitEvent(st, p->evFused[par], 0));
     PCUDA(launch_preprocess(c, d_depth, p->verts[par], p->normals[par], p->depthf[par], st));   // Application.cpp:73
     if (afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, st));      // the raw depth buffer may be overwritten from here on
     p->launches += (c->v.bilatLut != nullptr && c->cfg.policy == VH_POLICY_FIXED) ? 2 : 1;   // [k_bilateral +] k_preprocess
     const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
     int n = 0;
     if (p->overlap && st != nullptr) {
-        // caller's stream:  preprocess(k) -> ICP(k) x iterations -> [wait fusion(k-1)] -> pose_k, frame constants
-        // fusion stream:    [wait pose_k] -> alloc(k) -> compact -> integrate(k)
-        // The next push puts preprocess(k+1) + ICP(k+1) on the caller's stream right behind pose_k, beside fusion(k):
-        // the single-CTA tail of every ICP iteration (reduction + 6x6 solve) leaves the other SMs to the fusion kernels.
-        auto captured = [&](cudaStream_t cs, bool icp, cudaGraph_t* g, cudaGraphExec_t* ex, bool* have, int* cnt) -> int {
-            if (!*have) {
-                PCUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-                cudaError_t e = icp ? enqueueIcp(p, par, cs, cnt) : enqueueFusion(p, par, cs, cnt);
-                cudaError_t e2 = cudaStreamEndCapture(cs, g);
-                if (e != cudaSuccess) return pfail(VH_ERR_CUDA, "pipeline capture", e);
-                if (e2 != cudaSuccess) return pfail(VH_ERR_CUDA, "cudaStreamEndCapture", e2);
-                PCUDA(cudaGraphInstantiate(ex, *g, 0));
-                *have = true;
-            } else {
-                *cnt = icp ? 1 : 3 + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
-            }
-            PCUDA(cudaGraphLaunch(*ex, cs));
-            return VH_OK;
-        };
         int nIcp = 0, nFuse = 0;
-        if (track) { int rc = captured(st, true, &p->graph[par], &p->exec[par], &p->haveGraph[par], &nIcp); if (rc != VH_OK) return rc; }
-        if (p->fusePending) PCUDA(cudaStreamWaitEvent(st, p->evFused, 0));   // frame constants / counters are about to change
-        PCUDA(launch_set_frame_device(c, p->d_pose, track ? c->icp->delta : nullptr, track ? p->d_pose : nullptr, st));
-        PCUDA(cudaEventRecord(p->evPose, st));
-        PCUDA(cudaStreamWaitEvent(p->fuseStream, p->evPose, 0));
-        { int rc = captured(p->fuseStream, false, &p->fuseGraph[par], &p->fuseExec[par], &p->haveFuseGraph[par], &nFuse); if (rc != VH_OK) return rc; }
-        PCUDA(cudaEventRecord(p->evFused, p->fuseStream));
+        if (track) {
+            PCUDA(cudaEventRecord(p->evPre, st));
+            PCUDA(cudaStreamWaitEvent(p->trackStream, p->evPre, 0));
+            float* next = p->d_poseBuf[p->poseIdx ^ 1];
+            PCUDA(enqueueIcp(p, par, p->d_pose, next, p->trackStream, &nIcp));   // CameraTracking.cpp:35-67 + the pose chain
+            p->poseIdx ^= 1;
+            p->d_pose = next;
+            PCUDA(cudaEventRecord(p->evAligned, p->trackStream));
+            PCUDA(cudaStreamWaitEvent(st, p->evAligned, 0));               // the caller's stream is ordered behind the pose
+        } else {
+            PCUDA(cudaEventRecord(p->evAligned, st));
+        }
+        PCUDA(cudaStreamWaitEvent(p->fuseStream, p->evAligned, 0));
+        PCUDA(launch_set_frame_device(c, p->d_pose, nullptr, nullptr, p->fuseStream));   // SDF_Hashtable.cpp:15-21
+        if (!p->haveFuseGraph[par]) {
+            PCUDA(cudaStreamBeginCapture(p->fuseStream, cudaStreamCaptureModeThreadLocal));
+            cudaError_t e = enqueueFusion(p, par, p->fuseStream, &nFuse);
+            cudaError_t e2 = cudaStreamEndCapture(p->fuseStream, &p->fuseGraph[par]);
+            if (e != cudaSuccess) return pfail(VH_ERR_CUDA, "pipeline capture", e);
+            if (e2 != cudaSuccess) return pfail(VH_ERR_CUDA, "cudaStreamEndCapture", e2);
+            PCUDA(cudaGraphInstantiate(&p->fuseExec[par], p->fuseGraph[par], 0));
+            p->haveFuseGraph[par] = true;
+        } else {
+            nFuse = 3 + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
+        }
+        PCUDA(cudaGraphLaunch(p->fuseExec[par], p->fuseStream));
+        PCUDA(cudaEventRecord(p->evFused[par], p->fuseStream));
         p->fusePending = true;
+        p->lastFusePar = par;
         n = nIcp + 1 + nFuse;
     } else if (track && p->useGraph && st != nullptr) {
         // frame-to-model always reads maps[par] too, so keep one graph per parity in both modes
@@ -290,14 +318,14 @@ int vh_pipeline_push_host(vh_pipeline* p, const uint16_t* h_depth, float* h_pose
 // Overlapped schedule only: make stream s wait for the fusion of the latest pushed frame (a no-op otherwise).
 int vh_pipeline_flush(vh_pipeline* p, vh_stream s) {
     if (!p) return pfail(VH_ERR_INVALID, "vh_pipeline_flush: null pipeline");
-    if (p->fusePending) PCUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(s), p->evFused, 0));
+    if (p->fusePending) PCUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(s), p->evFused[p->lastFusePar], 0));
     return VH_OK;
 }
 
 int vh_pipeline_pose(vh_pipeline* p, float* pose16, vh_stream s) {
     if (!p || !pose16) return pfail(VH_ERR_INVALID, "vh_pipeline_pose: null argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
-    if (p->fusePending) PCUDA(cudaStreamWaitEvent(st, p->evFused, 0));
+    if (p->fusePending) PCUDA(cudaStreamWaitEvent(st, p->evFused[p->lastFusePar], 0));
     PCUDA(cudaMemcpyAsync(pose16, p->d_pose, 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
     PCUDA(cudaStreamSynchronize(st));
     return VH_OK;
