@@ -232,6 +232,16 @@ int vh_icp_iterate(vh_context* ctx, const float4* d_input, const float4* d_input
 /* maxIters iterations (ref Align). */
 int vh_icp_align(vh_context* ctx, const float4* d_input, const float4* d_inputNormals,
                  const float4* d_target, const float4* d_targetNormals, int iterations, vh_stream s);
+/* The tracking of one frame in ONE persistent launch (SURVEY.md section 8 f1 + f2): the pre-processing of the raw u16
+ * frame (ref preProcess, Application.cpp:73), the whole Align against d_target / d_targetNormals (ref
+ * CameraTracking.cpp:26-69) and, if the pose pointers are given, the chain d_pose_out = d_pose_in * delta (ref
+ * getTransform -> integrate, Application.cpp:75-84; the two may alias).  d_verts / d_normals / d_depthf are OUTPUTS:
+ * the same maps vh_preprocess writes (bit-identical) -- they are the next frame's target and the fusion's input.
+ * On a context with peers (vh_set_peers) this rank reduces its share of the image rows.  Not available with the
+ * bilateral front end. */
+int vh_track_frame(vh_context* ctx, const uint16_t* d_depth, float4* d_verts, float4* d_normals, float* d_depthf,
+                   const float4* d_target, const float4* d_targetNormals, int iterations,
+                   const float* d_pose_in, float* d_pose_out, vh_stream s);
 /* Reduction only (no solve): writes one vh_icp_system to d_system. Rows [row0,row1) of the
  * image only -- the multi-GPU split. */
 int vh_icp_reduce(vh_context* ctx, const float4* d_input, const float4* d_inputNormals,

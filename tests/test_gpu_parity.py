@@ -5,6 +5,7 @@ TSDF within 1e-5 absolute (bit-exact is asserted where the arithmetic is determi
 ICP normal equations relative 1e-5; pose within 1e-4 in rotation and translation.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -357,6 +358,49 @@ def test_icp_align_pose(built_library, oracle, policy):
     assert rot_err(g2[:3, :3], odelta2[:3, :3]) <= 1e-4 and np.max(np.abs(g2[:3, 3] - odelta2[:3, 3])) <= 1e-4
 
 
+def test_track_frame_is_preprocess_plus_align_plus_pose_chain(built_library, oracle):
+    """vh_track_frame (one persistent launch: pre-processing prologue, Align, pose chain) == vh_preprocess + vh_icp_align +
+    pose * delta, bit for bit, for both policies; the maps it leaves behind are the oracle's."""
+    for policy in (POLICY_REF_EXACT, POLICY_FIXED):
+        cfg = Config(policy=policy, icpNormalThres=0.8 if policy == POLICY_FIXED else -1.0)
+        d0 = render(cfg, scenes.scene_S1T(), scenes.trajectory_C2(0))
+        d1 = render(cfg, scenes.scene_S1T(), scenes.trajectory_C2(10))
+        d1[100:130, 200:260] = 0
+        pose0 = scenes.trajectory_C2(0).astype(np.float32)
+        a, b = Context(cfg), Context(cfg)
+        tv, tn, _ = gpu_preprocess(a, d0)
+        # separate launches
+        v1, n1, f1 = gpu_preprocess(a, d1)
+        a.icp_reset(True)
+        a.icp_align(v1, n1, tv, tn, 12)
+        delta_a = a.icp_get()[0]
+        # fused
+        v2, n2, f2 = b.new_maps()
+        p_in, p_out = cu(pose0.reshape(-1)), torch.zeros(16, device="cuda")
+        b.icp_reset(True)
+        b.track_frame(cu(d1.reshape(-1)), v2, n2, f2, tv, tn, 12, p_in, p_out)
+        torch.cuda.synchronize()
+        delta_b = b.icp_get()[0]
+        for x, y in ((v1, v2), (n1, n2), (f1, f2)):
+            assert np.array_equal(bits(x.cpu().numpy()), bits(y.cpu().numpy()))
+        ov, on, odf = oracle.OracleTable(cfg).preprocess(d1)
+        assert np.array_equal(bits(v2.cpu().numpy()), bits(ov)) and np.array_equal(bits(n2.cpu().numpy()), bits(on))
+        assert np.array_equal(bits(delta_a), bits(delta_b))
+        want = np.zeros((4, 4), np.float32)
+        for r in range(4):                                  # k_set_frame's products, left to right, no contraction
+            for c in range(4):
+                t = np.float32(pose0[r, 0] * delta_b[0, c])
+                for k in (1, 2, 3):
+                    t = np.float32(t + np.float32(pose0[r, k] * delta_b[k, c]))
+                want[r, c] = t
+        assert np.array_equal(bits(p_out.cpu().numpy().reshape(4, 4)), bits(want))
+        # in place (pose_out aliases pose_in)
+        b.icp_reset(True)
+        b.track_frame(cu(d1.reshape(-1)), v2, n2, f2, tv, tn, 12, p_in, p_in)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(p_in.cpu().numpy().reshape(4, 4)), bits(want))
+
+
 def test_linear_system_300_contract(built_library, oracle):
     """buildLinearSystemOnDevice (the un-built LinearSystem.cu reducer): 300 x 27 partials whose sum is
     A^T A | A^T b with A = (s x n, n), b = n.d - n.s."""
@@ -487,7 +531,8 @@ def test_pipeline_tracks_synthetic_trajectory(built_library, oracle):
     frames = [cu(render(cfg, scenes.scene_S1T(), p).reshape(-1)) for p in poses]
     results = []
     models = []
-    for use_graph, overlap in ((True, False), (False, False), (True, True)):
+    for use_graph, overlap, fused_pre in ((True, False, False), (False, False, False), (True, True, False), (True, True, True)):
+        os.environ["VH_PIPE_FUSED_PRE"] = "1" if fused_pre else "0"      # read at pipeline creation
         ctx = Context(cfg)
         pipe = FramePipeline(ctx, iterations=10, mode=FramePipeline.FRAME_TO_FRAME, use_graph=use_graph, overlap=overlap)
         s = torch.cuda.Stream()
@@ -506,7 +551,10 @@ def test_pipeline_tracks_synthetic_trajectory(built_library, oracle):
     for r in results[1:]:                                   # plain launches and the overlapped schedule: same bits
         assert np.array_equal(bits(results[0][0]), bits(r[0]))
         assert results[0][1:3] == r[1:3]
-        assert results[0][3] == r[3] == 40 + 39 * (1 + 1) + 40 * 3 + 1      # preprocess, Align + pose, fusion, first pose
+    # kernels per frame: preprocess, Align, frame constants, alloc + compact + integrate
+    assert results[0][3] == results[1][3] == results[2][3] == 40 + 39 + 40 + 40 * 3
+    assert results[3][3] == 1 + 39 + 40 + 40 * 3              # pre-processing of the tracked frames inside the Align kernel
+    os.environ.pop("VH_PIPE_FUSED_PRE", None)
     for m in models[1:]:
         exact, _ = compare_blocks(m, models[0])
         assert exact

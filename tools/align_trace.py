@@ -41,7 +41,10 @@ with torch.cuda.stream(s):
         ctx.icp_reset(True, s)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(s)
-        ctx.icp_align(b[0], b[1], a[0], a[1], 20, s)
+        if "pre" in sys.argv:
+            ctx.track_frame(d[1], b[0], b[1], b[2], a[0], a[1], 20, None, None, s)
+        else:
+            ctx.icp_align(b[0], b[1], a[0], a[1], 20, s)
         e1.record(s)
         s.synchronize()
         print("align x20 by events: %.1f us" % (e0.elapsed_time(e1) * 1e3))
@@ -49,6 +52,11 @@ with torch.cuda.stream(s):
     lib.vh_align_trace_read.argtypes = [C.c_void_p, C.c_int]
     lib.vh_align_trace_read(tr.ctypes.data, tr.size)
 tr = tr.reshape(1024, IT, SL).astype(np.int64)
+if "pre" in sys.argv:
+    pr = tr[: int((tr[:, 23, 0] > 0).sum()), 23]
+    t00 = pr[:, 0].min()
+    print("prologue: start spread %d ns; maps written: median %d max %d ns; after fence + barrier + fence: median %d max %d ns" % (
+        pr[:, 0].max() - t00, np.median(pr[:, 1] - t00), (pr[:, 1] - t00).max(), np.median(pr[:, 2] - t00), (pr[:, 2] - t00).max()))
 n = int((tr[:, 0, 0] > 0).sum())
 tr = tr[:n, :20]
 print("CTAs", n)

@@ -5,24 +5,9 @@
 // Here one kernel reads the 2-byte depth of the pixel and of its four neighbours (L1-resident),
 // recomputes the five back-projections in registers -- the same operations in the same order, so
 // the results are bit-identical to the two-pass form -- and writes 36 B per pixel.
-#include "vh_device.cuh"
+#include "preprocess_device.cuh"
 
 namespace vh {
-
-// Depth of pixel (x, y) in metres.  SMOOTH (Fixed, optional): from the bilateral-filtered image.
-template <class P, bool SMOOTH>
-__device__ __forceinline__ float metricDepth(const View& v, const uint16_t* __restrict__ depth, int x, int y) {
-    const size_t i = (size_t)y * v.W + x;
-    float d = (SMOOTH ? __ldg(v.depthSmooth + i) : (float)__ldg(depth + i)) / v.depthScale;     // ref :63-64
-    if (P::fixed && !(d > v.depthMin && d < v.depthMax)) d = 0.0f;
-    return d;
-}
-template <class P, bool SMOOTH>
-__device__ __forceinline__ float3 backproject(const View& v, const uint16_t* __restrict__ depth, int x, int y) {
-    const float d = metricDepth<P, SMOOTH>(v, depth, x, y);
-    float3 k = mul3(v.Kinv, (float)x, (float)y, 1.0f);                        // ref :69-70
-    return make_float3(k.x * d, k.y * d, k.z * d);
-}
 
 // Optional front end (Fixed): 5x5 bilateral filter of the raw depth.  Spatial weight
 // g[|dy|] * g[|dx|], range weight from a table indexed by the depth difference in raw units (both tables are computed
@@ -65,38 +50,7 @@ __global__ void __launch_bounds__(256) k_preprocess(View v, const uint16_t* __re
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= v.W || y >= v.H) return;
-    const size_t idx = (size_t)y * v.W + x;
-    const float3 CC = backproject<P, SMOOTH>(v, depth, x, y);
-    verts[idx] = make_float4(CC.x, CC.y, CC.z, 1.0f);                         // ref :72-73, w = 1 always (Q27)
-    if (depthf) {                                                             // integration reads the RAW depth
-        float3 kz = mul3(v.Kinv, (float)x, (float)y, 1.0f);
-        depthf[idx] = SMOOTH ? kz.z * metricDepth<P, false>(v, depth, x, y) : CC.z;
-    }
-    float4 n = make_float4(0.f, 0.f, 0.f, 0.f);                               // ref :91
-    if (x > 0 && x < v.W - 1 && y > 0 && y < v.H - 1) {                       // ref :93
-        const float3 PC = backproject<P, SMOOTH>(v, depth, x, y + 1);
-        const float3 CP = backproject<P, SMOOTH>(v, depth, x + 1, y);
-        const float3 MC = backproject<P, SMOOTH>(v, depth, x, y - 1);
-        const float3 CM = backproject<P, SMOOTH>(v, depth, x - 1, y);
-        bool ok;
-        if (!P::fixed) {
-            ok = CC.x != 0 && PC.x != 0 && CP.x != 0 && MC.x != 0 && CM.x != 0;   // ref :100 (tests .x)
-        } else {
-            ok = CC.z != 0 && PC.z != 0 && CP.z != 0 && MC.z != 0 && CM.z != 0;
-            if (ok) {
-                float lim = 0.05f * CC.z;
-                ok = fabsf(PC.z - CC.z) < lim && fabsf(MC.z - CC.z) < lim && fabsf(CP.z - CC.z) < lim && fabsf(CM.z - CC.z) < lim;
-            }
-        }
-        if (ok) {
-            float ax = PC.x - MC.x, ay = PC.y - MC.y, az = PC.z - MC.z;       // ref :102
-            float bx = CP.x - CM.x, by = CP.y - CM.y, bz = CP.z - CM.z;
-            float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;   // helper_math.h:1420
-            float l = sqrtf(nx * nx + ny * ny + nz * nz);                     // helper_math.h:1291
-            if (l > 0.0f) n = make_float4(nx / l, ny / l, nz / l, 0.0f);      // ref :105-109
-        }
-    }
-    normals[idx] = n;
+    preprocessPixel<P, SMOOTH>(v, depth, x, y, verts, normals, depthf);
 }
 
 cudaError_t launch_preprocess(vh_context* c, const uint16_t* depth, float4* verts, float4* normals, float* depthf,

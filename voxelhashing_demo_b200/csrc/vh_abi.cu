@@ -363,7 +363,20 @@ int vh_icp_align(vh_context* c, const float4* in, const float4* inN, const float
                  vh_stream s) {
     if (!c || !in || !tg || !tgN) return fail(VH_ERR_INVALID, "vh_icp_align: null argument");
     if (iterations <= 0) iterations = c->cfg.icpIterations;
-    VH_CUDA(launch_icp_align(c, in, inN, tg, tgN, 0, c->v.H, iterations, false, nullptr, nullptr, S(s)));   // CameraTracking.cpp:35-67, one launch
+    VH_CUDA(launch_icp_align(c, nullptr, nullptr, in, inN, tg, tgN, 0, c->v.H, iterations, false, nullptr, nullptr, S(s)));   // CameraTracking.cpp:35-67, one launch
+    return VH_OK;
+}
+// Pre-processing + Align + pose chain of one frame in ONE launch (k_track.cu).
+int vh_track_frame(vh_context* c, const uint16_t* d_depth, float4* d_verts, float4* d_normals, float* d_depthf, const float4* tg,
+                   const float4* tgN, int iterations, const float* d_pose_in, float* d_pose_out, vh_stream s) {
+    if (!c || !d_depth || !d_verts || !d_normals || !d_depthf || !tg || !tgN) return fail(VH_ERR_INVALID, "vh_track_frame: null argument");
+    if ((d_pose_in == nullptr) != (d_pose_out == nullptr)) return fail(VH_ERR_INVALID, "vh_track_frame: pose_in and pose_out go together");
+    if (c->v.bilatLut != nullptr) return fail(VH_ERR_UNSUPPORTED, "vh_track_frame: the bilateral front end needs its own pass (vh_preprocess + vh_icp_align)");
+    if (iterations <= 0) iterations = c->cfg.icpIterations;
+    const int world = c->peers.world > 1 ? c->peers.world : 1, rank = world > 1 ? c->peers.rank : 0;
+    const int base = c->v.H / world, rem = c->v.H % world;
+    const int row0 = rank * base + (rank < rem ? rank : rem), row1 = row0 + base + (rank < rem ? 1 : 0);
+    VH_CUDA(launch_icp_align(c, d_depth, d_depthf, d_verts, d_normals, tg, tgN, row0, row1, iterations, world > 1, d_pose_in, d_pose_out, S(s)));
     return VH_OK;
 }
 int vh_icp_reduce(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN, int row0, int row1,
@@ -391,7 +404,7 @@ int vh_icp_align_rows(vh_context* c, const float4* in, const float4* inN, const 
     if (!c || !in || !tg || !tgN) return fail(VH_ERR_INVALID, "vh_icp_align_rows: null argument");
     if (row0 < 0 || row1 > c->v.H || row0 > row1) return fail(VH_ERR_INVALID, "vh_icp_align_rows: bad row range");
     if (iterations <= 0) iterations = c->cfg.icpIterations;
-    VH_CUDA(launch_icp_align(c, in, inN, tg, tgN, row0, row1, iterations, c->peers.world > 1, nullptr, nullptr, S(s)));
+    VH_CUDA(launch_icp_align(c, nullptr, nullptr, in, inN, tg, tgN, row0, row1, iterations, c->peers.world > 1, nullptr, nullptr, S(s)));
     return VH_OK;
 }
 

@@ -142,11 +142,12 @@ cudaError_t launch_icp_iter_ex(vh_context* c, const float4* in, const float4* in
                                int row0, int row1, vh_icp_system* d_out, bool solve, bool first, bool chained, cudaStream_t s);
 cudaError_t launch_icp_solve(vh_context* c, const vh_icp_system* d_sys, cudaStream_t s);
 // whole Align in one persistent cooperative launch (k_track.cu); peers: fuse the cross-GPU all-reduce (vh_set_peers);
+// d_depth (optional): fused pre-processing -- the prologue turns the raw frame into the maps in / inN / d_depthf (which
+// it WRITES) before tracking them against tg / tgN;
 // d_poseOut (optional, may alias d_poseIn): 16 floats, row-major camera -> world, = d_poseIn * delta at the end of the launch
-cudaError_t launch_icp_align(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
-                             int row0, int row1, int iterations, bool peers, const float* d_poseIn, float* d_poseOut, cudaStream_t s);
-cudaError_t launch_icp_iter_peer(vh_context* c, const float4* in, const float4* inN, const float4* tg, const float4* tgN,
-                                 int row0, int row1, bool first, cudaStream_t s);
+cudaError_t launch_icp_align(vh_context* c, const uint16_t* d_depth, float* d_depthf, const float4* in, const float4* inN,
+                             const float4* tg, const float4* tgN, int row0, int row1, int iterations, bool peers,
+                             const float* d_poseIn, float* d_poseOut, cudaStream_t s);
 cudaError_t launch_icp_reset(vh_context* c, bool resetDelta, cudaStream_t s);
 cudaError_t launch_icp_set_twist(vh_context* c, const float* twist6, cudaStream_t s);
 cudaError_t launch_icp_twist(vh_context* c, cudaStream_t s);

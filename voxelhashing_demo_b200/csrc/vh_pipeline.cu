@@ -17,6 +17,7 @@
 // On a partitioned context with peer mailboxes (vh_set_peers) the Align kernel reduces this rank's image rows and
 // carries the cross-GPU all-reduce inside.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -48,6 +49,7 @@ struct vh_pipeline {
     bool haveGraph[2];
     // overlapped schedule (VH_PIPE_OVERLAP): fusion of frame k runs on its own stream beside preprocess + ICP of frame k+1
     bool overlap;
+    bool fusedPre;                 // VH_PIPE_FUSED_PRE=1: pre-processing inside the Align kernel (see pushFrame)
     cudaStream_t fuseStream, trackStream;
     cudaEvent_t evPre;
     cudaEvent_t evAligned, evFused[2];
@@ -68,7 +70,7 @@ int pfail(int code, const char* what, cudaError_t e = cudaSuccess) {
 }
 #define PCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return pfail(VH_ERR_CUDA, #expr, _e); } while (0)
 
-cudaError_t enqueueIcp(vh_pipeline* p, int par, const float* d_poseIn, float* d_poseOut, cudaStream_t s, int* n) {
+cudaError_t enqueueIcp(vh_pipeline* p, int par, const uint16_t* d_depth, const float* d_poseIn, float* d_poseOut, cudaStream_t s, int* n) {
     vh_context* c = p->ctx;
     const float4* tg = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelVerts : p->verts[1 - par];
     const float4* tgN = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelNormals : p->normals[1 - par];
@@ -78,7 +80,8 @@ cudaError_t enqueueIcp(vh_pipeline* p, int par, const float* d_poseIn, float* d_
     const int base = c->v.H / world, rem = c->v.H % world;
     const int row0 = rank * base + (rank < rem ? rank : rem), row1 = row0 + base + (rank < rem ? 1 : 0);
     // CameraTracking.cpp:35-67: the whole iteration loop is one persistent kernel (k_track.cu)
-    cudaError_t e = launch_icp_align(c, p->verts[par], p->normals[par], tg, tgN, row0, row1, p->iterations, world > 1, d_poseIn, d_poseOut, s);
+    cudaError_t e = launch_icp_align(c, d_depth, d_depth ? p->depthf[par] : nullptr, p->verts[par], p->normals[par], tg, tgN, row0, row1,
+                                     p->iterations, world > 1, d_poseIn, d_poseOut, s);
     if (e != cudaSuccess) return e;
     *n = 1;
     return cudaSuccess;
@@ -106,7 +109,7 @@ cudaError_t enqueueBody(vh_pipeline* p, int par, bool track, cudaStream_t s, int
     int k = 0;
     const float4* in = p->verts[par];
     if (track) {
-        e = enqueueIcp(p, par, nullptr, nullptr, s, &k);
+        e = enqueueIcp(p, par, nullptr, nullptr, nullptr, s, &k);
         if (e != cudaSuccess) return e;
         e = launch_set_frame_device(c, p->d_pose, c->icp->delta, p->d_pose, s);   // T_k = T_{k-1} * delta
     } else {
@@ -148,6 +151,7 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
     p->useGraph = (useGraph & VH_PIPE_GRAPH) != 0;
     // the overlapped schedule needs a model-independent ICP target (frame-to-frame) and the graph path
     p->overlap = (useGraph & VH_PIPE_OVERLAP) != 0 && p->useGraph && mode == VH_TRACK_FRAME_TO_FRAME;
+    { const char* env = getenv("VH_PIPE_FUSED_PRE"); p->fusedPre = env && env[0] == '1'; }
     const size_t px = (size_t)ctx->v.W * ctx->v.H;
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
@@ -228,24 +232,34 @@ int vh_pipeline_reset(vh_pipeline* p, const float* pose16_host, vh_stream s) {
 static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, cudaEvent_t afterPreprocess) {
     vh_context* c = p->ctx;
     const int par = (int)(p->frame & 1);
+    const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
     // overlapped schedule: the maps of this parity were read by the fusion of frame k-2 on the other stream
     if (p->overlap && st != nullptr && p->frame >= 2) PCUDA(cudaStreamWaitEvent(st, p->evFused[par], 0));
-    PCUDA(launch_preprocess(c, d_depth, p->verts[par], p->normals[par], p->depthf[par], st));   // Application.cpp:73
-    if (afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, st));      // the raw depth buffer may be overwritten from here on
-    p->launches += (c->v.bilatLut != nullptr && c->cfg.policy == VH_POLICY_FIXED) ? 2 : 1;   // [k_bilateral +] k_preprocess
-    const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
+    // Tracked frames of the overlapped schedule CAN run the pre-processing as the prologue of the Align kernel
+    // (k_track.cu, vh_track_frame).  Measured at VGA (r2, tools/align_trace.py pre): the prologue needs 7.4 us at the
+    // persistent kernel's 16 warps per SM (5 IEEE divisions + a normalisation per pixel) + 2.7 us of fence / barrier /
+    // fence, against ~5 us for the stand-alone pass at full occupancy + one stream hand-off: 7 820 vs 8 450 frames/s.
+    // So it is opt-in (VH_PIPE_FUSED_PRE=1); the stand-alone pass stays the default.
+    const bool fusedPre = p->fusedPre && p->overlap && st != nullptr && track && c->v.bilatLut == nullptr;
+    if (!fusedPre) {
+        PCUDA(launch_preprocess(c, d_depth, p->verts[par], p->normals[par], p->depthf[par], st));   // Application.cpp:73
+        if (afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, st));  // the raw depth buffer may be overwritten from here on
+        p->launches += (c->v.bilatLut != nullptr && c->cfg.policy == VH_POLICY_FIXED) ? 2 : 1;   // [k_bilateral +] k_preprocess
+    }
     int n = 0;
     if (p->overlap && st != nullptr) {
         int nIcp = 0, nFuse = 0;
         if (track) {
-            PCUDA(cudaEventRecord(p->evPre, st));
+            PCUDA(cudaEventRecord(p->evPre, st));                          // the frame (and, unfused, its maps) are ready
             PCUDA(cudaStreamWaitEvent(p->trackStream, p->evPre, 0));
             float* next = p->d_poseBuf[p->poseIdx ^ 1];
-            PCUDA(enqueueIcp(p, par, p->d_pose, next, p->trackStream, &nIcp));   // CameraTracking.cpp:35-67 + the pose chain
+            // Application.cpp:73-75 + CameraTracking.cpp:35-67 + the pose chain, one launch
+            PCUDA(enqueueIcp(p, par, fusedPre ? d_depth : nullptr, p->d_pose, next, p->trackStream, &nIcp));
             p->poseIdx ^= 1;
             p->d_pose = next;
             PCUDA(cudaEventRecord(p->evAligned, p->trackStream));
             PCUDA(cudaStreamWaitEvent(st, p->evAligned, 0));               // the caller's stream is ordered behind the pose
+            if (fusedPre && afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, st));
         } else {
             PCUDA(cudaEventRecord(p->evAligned, st));
         }

@@ -263,6 +263,11 @@ class Context:
     def peer_bytes(self) -> int:
         return int(self.lib.vh_peer_bytes())
 
+    def track_frame(self, depth_u16, verts, normals, depthf, tgt, tgtN, iterations=0, pose_in=None, pose_out=None, stream=None):
+        """Pre-processing + Align (+ pose chain) of one frame in one persistent launch; verts / normals / depthf are outputs."""
+        L.check(self.lib.vh_track_frame(self._h, _ptr(depth_u16), _ptr(verts), _ptr(normals), _ptr(depthf), _ptr(tgt), _ptr(tgtN),
+                                        iterations, _ptr(pose_in), _ptr(pose_out), _stream(stream)), "vh_track_frame")
+
     def icp_align_rows(self, inp, inpN, tgt, tgtN, row0, row1, iterations=0, stream=None):
         L.check(self.lib.vh_icp_align_rows(self._h, _ptr(inp), _ptr(inpN), _ptr(tgt), _ptr(tgtN), row0, row1, iterations,
                                            _stream(stream)), "vh_icp_align_rows")

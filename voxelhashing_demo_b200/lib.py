@@ -103,7 +103,7 @@ HANDLE_SYMBOLS = [
     "vh_last_error", "vh_default_config", "vh_device_count", "vh_create", "vh_destroy", "vh_reset", "vh_get_config",
     "vh_set_intrinsics", "vh_set_intrinsic_matrices", "vh_bytes_allocated", "vh_preprocess", "vh_set_pose",
     "vh_set_pose_device", "vh_alloc_blocks", "vh_alloc_blocks_depth", "vh_compact", "vh_integrate", "vh_integrate_depthf", "vh_fuse_frame",
-    "vh_get_stats", "vh_garbage_collect", "vh_stream_out", "vh_stream_in", "vh_icp_reset", "vh_icp_iterate", "vh_icp_align", "vh_icp_reduce", "vh_icp_solve", "vh_icp_get",
+    "vh_get_stats", "vh_garbage_collect", "vh_stream_out", "vh_stream_in", "vh_icp_reset", "vh_icp_iterate", "vh_icp_align", "vh_track_frame", "vh_icp_reduce", "vh_icp_solve", "vh_icp_get",
     "vh_icp_set_delta", "vh_set_peers", "vh_peer_bytes", "vh_icp_align_rows", "vh_icp_delta_device", "vh_pose_compose", "vh_icp_reduce_corr", "vh_find_correspondences",
     "vh_jacobians", "vh_raycast", "vh_export_entries", "vh_export_compact", "vh_export_block",
     "vh_compact_table_device", "vh_compact_counter_device", "vh_voxel_blocks_device", "vh_save", "vh_load",
@@ -156,6 +156,7 @@ def load_library() -> C.CDLL:
     lib.vh_icp_reset.argtypes = [P, I, P]
     lib.vh_icp_iterate.argtypes = [P, P, P, P, P, P]
     lib.vh_icp_align.argtypes = [P, P, P, P, P, I, P]
+    lib.vh_track_frame.argtypes = [P, P, P, P, P, P, P, I, P, P, P]
     lib.vh_icp_reduce.argtypes = [P, P, P, P, P, I, I, P, P]
     lib.vh_icp_solve.argtypes = [P, P, P]
     lib.vh_set_peers.argtypes = [P, I, I, C.POINTER(C.c_void_p)]
