@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the fusion-and-tracking hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C3|C4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C3|C4|C5]
 
 A "step" is one depth frame through the whole hot path: preprocess -> ICP (20 Gauss-Newton iterations,
 1 level) -> pose update -> block allocation -> visible-block compaction -> TSDF integration.
@@ -9,12 +9,19 @@ A "step" is one depth frame through the whole hot path: preprocess -> ICP (20 Ga
   N = 1 (default): config C2 of BASELINE.json -- 300-frame synthetic VGA sequence with known
         trajectory on one B200.  `value` = frames/s with all frames resident in HBM; `e2e` = the same
         through the public C ABI with HOST buffers (H2D of every depth frame, D2H of every pose).
-  N > 1: config C4 -- large-volume scene, block-hash space partitioned over the ranks
-        (owner = mix(block) mod N), depth frame broadcast over NVLink (NCCL), ICP image rows split
-        with one 32-float all-reduce per iteration.  Strong scaling: every rank works on the same frames.
+        The K-step pass is repeated (default 5x, each after its own W warm-up steps) and the MEDIAN is
+        reported, so a 3 ms timed region is not a single sample.
+  N > 1 (torchrun): config C4 AS BASELINE.json STATES IT -- building-scale scene at 2 mm voxels, block-hash
+        space partitioned over the ranks (owner = mix(block) mod N, per-GPU 1 048 576 blocks / 4 000 037
+        buckets), depth frame broadcast over NVLink, ICP image rows split with the 32-float all-reduce fused
+        into the persistent Align kernel over peer memory.  Strong scaling: every rank works on the same
+        frames; the line carries the SAME workload on one GPU (`single_gpu_same_workload`), the per-rank
+        integrate roofline, per-stage times and the cross-rank equivalence checks.
+        (A torchrun launch with WORLD_SIZE=1, or --workload C4, runs that workload on one GPU.)
   --impl reference: the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref/libvh_ref.so,
-        driven with the reference's own call sequence and host syncs) on the same frames; the CPU
-        transliteration (oracle/, OpenMP) is timed next to it.  The reference has no CPU path.
+        driven with the reference's own call sequence and host syncs) on the same frames and the same table
+        geometry (the reference has no CPU path); its printf-stripped and shipped -G builds and the CPU
+        transliteration (oracle/, OpenMP, 1 thread and all cores) are timed next to it.
 
 Prints ONE JSON line on rank 0.
 """
@@ -38,7 +45,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "VGA frames/s (alloc+integrate+ICP)"
 UNIT = "frames/s"
 
-# Libraries print to stdout behind our back (NCCL's version banner, the reference's std::cout and device
+# Libraries print to stdout behind our back (NCCL's banners, the reference's std::cout and device
 # printf).  The contract is ONE JSON line on stdout: keep the real stdout aside, point fd 1 at stderr.
 _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
@@ -49,28 +56,51 @@ def emit(obj) -> None:
 
 
 # ---------------------------------------------------------------------------------------------------
-def workload_config(name: str, part_count: int = 1, part_rank: int = 0):
+C4_VOXEL = 0.002                     # BASELINE.json configs[3]: "Building-scale synthetic scene at 2 mm voxels"
+C4_BLOCKS_PER_GPU = 1048576          # per-GPU numVoxelBlocks (4 GiB of voxels)
+C4_BLOCKS_SINGLE = 4000000           # one GPU holding the whole volume (ptr = id * 512 fits the reference's int)
+
+
+def workload_config(name: str, part_count: int = 1, part_rank: int = 0, policy=None):
     from voxelhashing_demo_b200 import POLICY_FIXED, Config, scenes
 
+    pol = POLICY_FIXED if policy is None else policy
     if name in ("C2", "C5"):
-        cfg = Config(policy=POLICY_FIXED, numBuckets=100003, bucketSize=5, numVoxelBlocks=65536, voxelSize=0.02,
-                     truncation=0.06, truncScale=0.01, overflowSlots=16384, icpNormalThres=0.8, icpIterations=20,
+        cfg = Config(policy=pol, numBuckets=100003, bucketSize=5, numVoxelBlocks=65536, voxelSize=0.02,
+                     truncation=0.06, truncScale=0.01, overflowSlots=16384 if pol == POLICY_FIXED else 0,
+                     icpNormalThres=0.8 if pol == POLICY_FIXED else -1.0, icpIterations=20,
                      partCount=part_count, partRank=part_rank)
         return cfg, scenes.scene_S1T(), scenes.trajectory_C2, 300
     if name == "C3":
-        cfg = Config(policy=POLICY_FIXED, width=1280, height=720, fx=1034.6, fy=1033.0, cx=637.2, cy=382.95,
+        cfg = Config(policy=pol, width=1280, height=720, fx=1034.6, fy=1033.0, cx=637.2, cy=382.95,
                      numBuckets=1000003, bucketSize=5, numVoxelBlocks=262144, voxelSize=0.005, truncation=0.02,
                      truncScale=0.0025, overflowSlots=131072, depthMax=8.0, maxIntegrationDistance=8.0,
                      icpNormalThres=0.8, icpIterations=20, partCount=part_count, partRank=part_rank)
         return cfg, scenes.scene_S2(), (lambda k: scenes.trans(0, 0, 0.3) @ scenes.trajectory_C3(k)), 1000
-    if name == "C4":
-        per_gpu_blocks = 1048576 if part_count > 1 else 2097152
-        cfg = Config(policy=POLICY_FIXED, width=1280, height=720, fx=1034.6, fy=1033.0, cx=637.2, cy=382.95,
-                     numBuckets=4000037, bucketSize=5, numVoxelBlocks=per_gpu_blocks, voxelSize=0.004, truncation=0.016,
-                     truncScale=0.002, overflowSlots=524288, depthMax=12.5, maxIntegrationDistance=12.5,
+    if name in ("C4", "C4_4mm"):
+        # C4: 2 mm voxels (1.6 cm blocks), truncation band 4 voxels + 0.1 % of the depth.  C4_4mm: the 4 mm variant the
+        # integrate roofline leg has used since r1 (1.46 GB visible set on one GPU).
+        vs = C4_VOXEL if name == "C4" else 0.004
+        blocks = (C4_BLOCKS_PER_GPU if part_count > 1 else C4_BLOCKS_SINGLE) if name == "C4" else 2097152
+        cfg = Config(policy=pol, width=1280, height=720, fx=1034.6, fy=1033.0, cx=637.2, cy=382.95,
+                     numBuckets=4000037, bucketSize=5, numVoxelBlocks=blocks, voxelSize=vs, truncation=4 * vs,
+                     truncScale=vs / 2, overflowSlots=524288, depthMax=12.5, maxIntegrationDistance=12.5,
                      icpNormalThres=0.8, icpIterations=20, partCount=part_count, partRank=part_rank)
         return cfg, scenes.scene_S3(), (lambda k: scenes.trans(0, 0, 0.5) @ scenes.trajectory_C3(k)), 200
     raise SystemExit(f"unknown workload {name}")
+
+
+def config_dict(name: str, cfg, n_unique: int) -> dict:
+    """The `config` object of the JSON line: the workload only (identical in the own arm and the reference arm)."""
+    what = {"C2": "C2: synthetic 640x480 sequence (analytic sphere+plane scene S1T, known trajectory, 300 frames)",
+            "C5": "C5: C2 tracked frame-to-MODEL (CUDA hash-table raycast in the loop)",
+            "C3": "C3: synthetic 1280x720 sequence (room scene S2, 5 mm voxels, 1000 frames)",
+            "C4": "C4: building-scale synthetic 1280x720 sequence (hall scene S3) at 2 mm voxels",
+            "C4_4mm": "C4 geometry at 4 mm voxels (integrate roofline leg)"}[name]
+    return {"workload": what, "frames_cycled": n_unique, "image": f"{cfg.width}x{cfg.height}", "voxel_m": cfg.voxelSize,
+            "table": f"{cfg.numBuckets}x{cfg.bucketSize} buckets", "truncation_m": cfg.truncation,
+            "icp": f"{cfg.icpIterations} iterations x 1 level",
+            "l2": f"inputs larger than L2: {n_unique} distinct u16 frames cycled (ping-pong); no L2 flush between steps"}
 
 
 def render_frames(cfg, scene, traj, count):
@@ -145,7 +175,7 @@ class ClockSampler:
 
 def ncu_traffic(kernel_prefix: str):
     """dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full capture (profiles/)."""
-    for f in sorted((ROOT / "profiles").glob("*_traffic.json"), reverse=True):
+    for f in sorted((ROOT / "profiles").glob("r*_traffic.json"), reverse=True):
         if f.name.startswith("r1a"):
             continue
         for k, v in json.loads(f.read_text()).get("bytes", {}).items():
@@ -178,17 +208,19 @@ def silence_stdout():
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_port_baseline(cfg, frames, poses0, budget_s=20.0, max_frames=40, threads=0):
+def cpu_port_baseline(cfg, frames, pose0, budget_s=12.0, max_frames=40, threads=0):
     """The host transliteration (oracle/, OpenMP) on a bounded sample of the same workload, timed on
     this box's cores: preprocess + 20-iteration Align + alloc + compact + integrate per frame."""
     from oracle import binding as ob
 
     lib = ob.oracle_lib()
+    all_cores = lib.vo_num_threads() if not threads else None
     if threads:
+        all_cores = lib.vo_num_threads()
         lib.vo_set_num_threads(threads)
     cores = lib.vo_num_threads()
     ot = ob.OracleTable(cfg)
-    pose = poses0.astype(np.float32)
+    pose = pose0.astype(np.float32)
     prev = None
     est = np.zeros(6, np.float32)
     done, t0 = 0, time.perf_counter()
@@ -204,16 +236,34 @@ def cpu_port_baseline(cfg, frames, poses0, budget_s=20.0, max_frames=40, threads
             break
     dt = time.perf_counter() - t0
     ot.close()
+    if threads and all_cores:
+        lib.vo_set_num_threads(all_cores)
     return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {done} frames of the workload ({dt:.1f} s): oracle/ C++ port, OpenMP x{cores}, "
                       f"preprocess + {cfg.icpIterations}-iteration Align + alloc + compact + integrate per frame"}
+
+
+def cpu_baselines(cfg, frames, pose0, budget_s=12.0):
+    """All cores (the `cpu_baseline` object) and one thread (both are reported)."""
+    allc = cpu_port_baseline(cfg, frames, pose0, budget_s=budget_s)
+    one = cpu_port_baseline(cfg, frames, pose0, budget_s=budget_s * 0.75, threads=1)
+    allc["one_thread"] = {"value": one["value"], "unit": UNIT, "cores": 1, "sample": one["sample"]}
+    return allc
+
+
+def median_passes(run_pass, repeats: int):
+    """run_pass() -> (ms, extra); returns (median ms, all ms, extra of the median pass)."""
+    res = [run_pass() for _ in range(max(1, repeats))]
+    order = sorted(range(len(res)), key=lambda i: res[i][0])
+    mid = order[len(order) // 2]
+    return res[mid][0], [r[0] for r in res], res[mid][1]
 
 
 # ---------------------------------------------------------------------------------------------------
 def run_own(args):
     import torch
 
-    from voxelhashing_demo_b200 import Context, FramePipeline, _build
+    from voxelhashing_demo_b200 import POLICY_REF_EXACT, Context, FramePipeline, _build
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,8 +274,9 @@ def run_own(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     _build.build()
-    if world > 1:
-        return run_multi(args, rank, world, local)
+    under_torchrun = "RANK" in os.environ and "WORLD_SIZE" in os.environ
+    if world > 1 or (under_torchrun and args.workload is None) or args.workload == "C4":
+        return run_partitioned(args, rank, world, local)
 
     name = args.workload or "C2"
     cfg, scene, traj, seq_len = workload_config(name)
@@ -239,56 +290,77 @@ def run_own(args):
     h_frames = torch.from_numpy(frames).pin_memory()                 # e2e: pinned host buffers
     h_pose = torch.zeros((W + K, 16), dtype=torch.float32).pin_memory()
     frame_bytes = frames.shape[1] * 2
-
-    ctx = Context(cfg)
     stream = torch.cuda.Stream()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def run_sequence(host: bool):
-        ctx.reset(stream)
-        mode = FramePipeline.FRAME_TO_MODEL if name == "C5" else FramePipeline.FRAME_TO_FRAME
-        pipe = FramePipeline(ctx, iterations=cfg.icpIterations, mode=mode, use_graph=True, overlap=bool(args.overlap))
-        with torch.cuda.stream(stream):
-            pipe.reset(poses[order[0]].astype(np.float32), stream)
-            for i in range(W):
-                (pipe.push_host(h_frames[order[i]], h_pose[i], stream) if host else pipe.push_device(d_frames[order[i]], stream))
-            stream.synchronize()
-            l0 = pipe.launches()
-            with ClockSampler(local) as cs:
-                torch.cuda.synchronize()
-                ev0.record(stream)
-                for i in range(W, W + K):
+    def sequence_runner(ctx, cfg_):
+        def run_sequence(host: bool, sample_clocks: bool = False):
+            ctx.reset(stream)
+            mode = FramePipeline.FRAME_TO_MODEL if name == "C5" else FramePipeline.FRAME_TO_FRAME
+            pipe = FramePipeline(ctx, iterations=cfg_.icpIterations, mode=mode, use_graph=True, overlap=bool(args.overlap))
+            with torch.cuda.stream(stream):
+                pipe.reset(poses[order[0]].astype(np.float32), stream)
+                for i in range(W):
                     (pipe.push_host(h_frames[order[i]], h_pose[i], stream) if host else pipe.push_device(d_frames[order[i]], stream))
-                pipe.flush(stream)                      # overlapped schedule: the last frame's fusion belongs to the timed region
-                ev1.record(stream)
+                pipe.flush(stream)
                 stream.synchronize()
-            ms = ev0.elapsed_time(ev1)
-            launches = pipe.launches() - l0
-            pose = pipe.pose(stream)
-        pipe.close()
-        return ms, launches, pose, cs.summary()
+                l0 = pipe.launches()
+                with (ClockSampler(local) if sample_clocks else contextlib.nullcontext()) as cs:
+                    torch.cuda.synchronize()
+                    ev0.record(stream)
+                    for i in range(W, W + K):
+                        (pipe.push_host(h_frames[order[i]], h_pose[i], stream) if host else pipe.push_device(d_frames[order[i]], stream))
+                    pipe.flush(stream)                      # overlapped schedule: the last frame's fusion belongs to the timed region
+                    ev1.record(stream)
+                    stream.synchronize()
+                ms = ev0.elapsed_time(ev1)
+                launches = pipe.launches() - l0
+                pose = pipe.pose(stream)
+            pipe.close()
+            return ms, (launches, pose, cs.summary() if sample_clocks else None)
+        return run_sequence
 
-    ms, launches, pose, clocks = run_sequence(host=False)
-    ms_e2e, _, pose_e2e, _ = run_sequence(host=True)
+    ctx = Context(cfg)
+    run_sequence = sequence_runner(ctx, cfg)
+    # clocks are sampled over ALL timed passes of the device-resident leg (one nvidia-smi stream around them)
+    with ClockSampler(local) as cs_all:
+        ms, passes, (launches, pose, _) = median_passes(lambda: run_sequence(False), args.repeats)
+    clocks = cs_all.summary()
+    clocks["note"] = f"sampled every 50 ms across the {len(passes)} timed passes (warm-ups between them included)"
+    ms_e2e, passes_e2e, (_, pose_e2e, _) = median_passes(lambda: run_sequence(True), args.repeats)
     truth = poses[order[-1]]
     pose_err = float(np.max(np.abs(pose[:3, 3] - truth[:3, 3])))
     st = ctx.stats()
 
     stages, roof = stage_timings(ctx, cfg, d_frames, poses, order, stream)
     hbm = integrate_hbm_roofline(stream) if not args.no_hbm else None
-    cpu = None if args.no_cpu else cpu_port_baseline(cfg, frames, poses[0])
+    ctx.close()
+
+    # the repo's OWN kernels in the reference's arithmetic (RefExact policy) on the same frames and table: the
+    # like-for-like leg next to the reference arm (same config, same policy)
+    refexact = None
+    if name == "C2" and not args.no_refexact:
+        cfg_r, _, _, _ = workload_config("C2", policy=POLICY_REF_EXACT)
+        ctx_r = Context(cfg_r)
+        run_r = sequence_runner(ctx_r, cfg_r)
+        ms_r, passes_r, (launches_r, _, _) = median_passes(lambda: run_r(False), min(3, args.repeats))
+        ms_re, _, _ = median_passes(lambda: run_r(True), min(3, args.repeats))
+        refexact = {"policy": "RefExact (the reference's as-built arithmetic, SURVEY.md Appendix A; parity-pinned to the reference's CUDA outputs)",
+                    "value": K / (ms_r / 1e3), "unit": UNIT, "ms_per_step": ms_r / K, "passes_ms": passes_r,
+                    "e2e": {"value": K / (ms_re / 1e3), "unit": UNIT}, "gpu_launches": int(launches_r)}
+        ctx_r.close()
+    cpu = None if args.no_cpu else cpu_baselines(cfg, frames, poses[0])
 
     out = {
         "metric": METRIC, "value": K / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: {n_unique}-frame synthetic {cfg.width}x{cfg.height} sequence ({'frame-to-MODEL tracking, raycast in the loop; ' if name == 'C5' else ''}analytic scene, known trajectory), "
-                               f"voxel {cfg.voxelSize} m, {cfg.numBuckets}x{cfg.bucketSize} buckets, {cfg.numVoxelBlocks} blocks, "
-                               f"ICP {cfg.icpIterations} iterations x 1 level, Fixed policy",
-                   "l2": f"inputs larger than L2: {n_unique} distinct u16 frames = {n_unique * frame_bytes / 1e6:.0f} MB cycled; the visible "
-                         f"voxel working set ({st.numVisible} blocks = {st.numVisible * 4096 / 1e6:.0f} MB) is L2-resident by the nature of a VGA stream",
-                   "final_pose_translation_error_m": pose_err, "visible_blocks": st.numVisible, "allocated_blocks": st.numAllocated,
-                   "voxel_updates_per_frame": int(st.numUpdated)},
+        "config": config_dict(name, cfg, n_unique),
+        "policy": "Fixed (corrected pipeline, DESIGN.md section 4; bit-exact against its own oracle, anchored to the analytic scene)",
+        "passes": {"repeats": len(passes), "timed_ms": passes, "e2e_timed_ms": passes_e2e, "reported": "median"},
+        "results": {"final_pose_translation_error_m": pose_err, "visible_blocks": st.numVisible, "allocated_blocks": st.numAllocated,
+                    "voxel_updates_per_frame": int(st.numUpdated),
+                    "e2e_pose_equals_device_resident_pose": bool(np.array_equal(pose.view(np.uint32), pose_e2e.view(np.uint32)))},
         "e2e": {"value": K / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": 64,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": int(launches),
@@ -299,71 +371,80 @@ def run_own(args):
     }
     if hbm:
         out["roofline_integrate_hbm"] = hbm
+    if refexact:
+        out["refexact_leg"] = refexact
     if cpu:
         out["cpu_baseline"] = cpu
     emit(out)
 
 
-def stage_timings(ctx, cfg, d_frames, poses, order, stream):
-    """Instrumented pass: each stage timed alone with CUDA events on the launching stream (median over
-    frames of the steady-state model).  Gives the per-kernel durations the roofline object needs."""
+def stage_timings(ctx, cfg, d_frames, poses, order, stream, reps: int = 8):
+    """Instrumented pass: each stage timed with CUDA events on the launching stream around `reps` back-to-back launches
+    (median over frames of the steady-state model), so launch latency is not counted as kernel time.  Gives the
+    per-kernel durations the roofline object needs."""
     import torch
 
     n = cfg.width * cfg.height
     maps = [ctx.new_maps(), ctx.new_maps()]
-    d_pose = torch.zeros(16, device="cuda")
-    acc = {k: [] for k in ("preprocess", "icp_iteration", "icp_align", "alloc", "compact", "integrate")}
+    acc = {k: [] for k in ("preprocess", "icp_align", "alloc", "compact", "integrate")}
     peak, which = peaks()
 
-    def timed(fn):
+    def timed(fn, r=reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()                                               # one untimed launch: the GPU is awake, caches as in steady state
         e0.record(stream)
-        fn()
+        for _ in range(r):
+            fn()
         e1.record(stream)
         stream.synchronize()
-        return e0.elapsed_time(e1) * 1e3
+        return e0.elapsed_time(e1) * 1e3 / r
 
     with torch.cuda.stream(stream):
-        ids = order[-min(len(order), 24):]
+        ids = order[-min(len(order), 12):]
         for j, fi in enumerate(ids):
             cur, prev = maps[j & 1], maps[1 - (j & 1)]
             acc["preprocess"].append(timed(lambda: ctx.preprocess(d_frames[fi], cur[0], cur[1], cur[2], stream)))
             if j > 0:
-                ctx.icp_reset(True, stream)
-                acc["icp_iteration"].append(timed(lambda: ctx.icp_iterate(cur[0], cur[1], prev[0], prev[1], stream)))
-                ctx.icp_reset(True, stream)
-                acc["icp_align"].append(timed(lambda: ctx.icp_align(cur[0], cur[1], prev[0], prev[1], cfg.icpIterations, stream)))
+                def align():
+                    ctx.icp_reset(True, stream)
+                    ctx.icp_align(cur[0], cur[1], prev[0], prev[1], cfg.icpIterations, stream)
+                acc["icp_align"].append(timed(align, 4))
             ctx.set_pose(poses[fi].astype(np.float32), stream)
             acc["alloc"].append(timed(lambda: ctx.alloc_blocks(cur[0], cur[1], stream)))
             acc["compact"].append(timed(lambda: ctx.compact(stream)))
             acc["integrate"].append(timed(lambda: ctx.integrate_depthf(cur[2], stream)))
         st = ctx.stats(stream)
     stages = {k: float(np.median(v)) for k, v in acc.items() if v}
-    # dominant kernel of the step: the fused ICP iteration (20 launches per frame)
-    icp_bytes = 48 * n                                               # SURVEY.md 8d: source vertex + gathered target vertex + normal
-    t_icp = stages["icp_align"] / cfg.icpIterations * 1e-6
+    stages["icp_iteration"] = stages["icp_align"] / cfg.icpIterations
+    stages["note"] = (f"CUDA events around {reps} back-to-back launches per sample (4 for the Align, each preceded by the 2 us k_icp_reset); "
+                      "inside the frame loop the fusion stages run on a second stream beside the Align of the next frame")
+    # dominant kernel of the step: the persistent Align kernel (one launch per frame, 20 Gauss-Newton iterations)
+    per_px = 64 if cfg.icpNormalThres > -1.0 else 48       # SURVEY.md 8d: source vertex + gathered target vertex + normal (+ source normal)
+    icp_bytes = per_px * n * cfg.icpIterations
+    t_icp = stages["icp_align"] * 1e-6
     ach = icp_bytes / t_icp / 1e9
     integ_bytes = 16 * int(st.numUpdated) + 16 * st.numVisible + 4 * n
-    roof = {"kernel": "k_icp_iter<Fixed>", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": ncu_traffic("k_icp_iter"), "peak_source": which,
-            "note": "dominant kernel of the step (20 launches per frame, ~90 % of the launch list): 48*W*H algorithmic bytes per launch / "
-                    "mean launch time over a 20-iteration Align (CUDA events on the launching stream).  Its 19.7 MB working set is "
-                    "L2-resident at VGA and the launch is latency-bound (two dependent L2 round trips, grid-wide reduction, 6x6 solve: "
-                    "see DESIGN.md 3.2), so the fraction of the HBM peak is low by construction; traffic is the cold-L2 ncu capture. "
-                    "The HBM-bound kernel of the path is k_integrate: roofline_integrate_hbm",
+    roof = {"kernel": "k_icp_align<Fixed> (persistent: one launch = one Align = 20 iterations)", "bound": "hbm", "achieved": ach, "peak": peak,
+            "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("k_icp_align"), "peak_source": which,
+            "algorithmic_bytes": icp_bytes, "us": stages["icp_align"],
+            "note": f"dominant kernel of the step (~85 % of the frame): {per_px} B x W x H x {cfg.icpIterations} iterations of algorithmic bytes per launch / "
+                    "launch time (CUDA events on the launching stream).  The 20 MB working set is L1/L2-resident at VGA -- `traffic` (ncu, "
+                    "cold L2) is ~1/16 of the algorithmic bytes -- so this is NOT an HBM utilisation: the kernel is bound by instruction issue "
+                    "in the association loop (ncu: 64 % issue utilisation there) and by the per-iteration exchange + 6x6 solve "
+                    "(DESIGN.md 3.2).  The HBM-bound kernel of the path is k_integrate: roofline_integrate_hbm",
             "integrate_c2": {"bytes": integ_bytes, "us": stages["integrate"], "GB/s": integ_bytes / (stages["integrate"] * 1e-6) / 1e9,
                              "note": "L2-resident working set: not an HBM fraction"}}
     return stages, roof
 
 
-def integrate_hbm_roofline(stream):
+def integrate_hbm_roofline(stream, name: str = "C4_4mm"):
     """Integration over a visible set larger than 2x L2 (config C4 geometry on one GPU): the HBM-bound regime
     north_star quotes its 60 % target on.  achieved = (16 N_upd + 16 N_vis + 4 W H) / t."""
     import torch
 
     from voxelhashing_demo_b200 import Context, scenes
 
-    cfg, scene, traj, _ = workload_config("C4")
+    cfg, scene, traj, _ = workload_config(name)
     ctx = Context(cfg)
     pose = traj(0).astype(np.float32)
     depth = scenes.render_depth(scene, pose, cfg.width, cfg.height, cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.depthScale)
@@ -402,9 +483,9 @@ def integrate_hbm_roofline(stream):
     ctx.close()
     return {"kernel": "k_integrate<Fixed,dense>", "bound": "hbm", "achieved": nbytes / t / 1e9, "peak": peak, "unit": "GB/s",
             "frac": nbytes / t / 1e9 / peak, "traffic": ncu_traffic("k_integrate"), "algorithmic_bytes": nbytes,
-            "peak_source": which, "us": t * 1e6,
+            "peak_source": which, "us": t * 1e6, "voxel_m": cfg.voxelSize,
             "visible_blocks": st.numVisible, "voxel_working_set_MB": st.numVisible * 4096 / 1e6, "voxels_updated": int(st.numUpdated),
-            "voxel_updates_per_s": int(st.numUpdated) / t,
+            "voxel_updates_per_s": int(st.numUpdated) / t, "dropped": st.dropped,
             "gc_scan": {"kernel": "k_gc (scope ALL, no ageing)", "bytes": 4096 * (st.numAllocated - freed), "us": float(np.mean(gc_times)) * 1e6,
                         "GB/s": 4096 * (st.numAllocated - freed) / float(np.mean(gc_times)) / 1e9,
                         "frac": 4096 * (st.numAllocated - freed) / float(np.mean(gc_times)) / 1e9 / peak, "released": int(freed)},
@@ -412,15 +493,17 @@ def integrate_hbm_roofline(stream):
 
 
 # ---------------------------------------------------------------------------------------------------
-def run_multi(args, rank, world, local):
+def run_partitioned(args, rank, world, local):
+    """Config C4 (2 mm) with the block-hash space partitioned over `world` GPUs (world = 1: the whole volume on one GPU)."""
     import torch
     import torch.distributed as dist
 
     from voxelhashing_demo_b200 import Context
     from voxelhashing_demo_b200.dist import PartitionedTracker
 
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name = args.workload or "C4"
     cfg, scene, traj, seq_len = workload_config(name, world, rank)
     K, W = args.steps, args.warmup
@@ -428,21 +511,51 @@ def run_multi(args, rank, world, local):
     from voxelhashing_demo_b200.scenes import pingpong
 
     order = [pingpong(i, n_unique) for i in range(W + K)]
+    frames = None
     if rank == 0:
         frames, poses = render_frames(cfg, scene, traj, n_unique)
         d_frames = torch.from_numpy(frames).cuda()
     else:
         poses = [traj(k) for k in range(n_unique)]
         d_frames = None
-    # the same workload on ONE GPU (rank 0, unpartitioned), so the strong-scaling factor can be read off one line
-    single = None
-    if rank == 0 and not args.no_single:
+    stream = torch.cuda.current_stream()
+
+    def timed_run(tracker, src, with_pose_readback=False, h_pose=None):
+        """W warm-up pushes, then K timed ones; returns (ms on this rank, host enqueue ms)."""
+        tracker.reset(poses[order[0]].astype(np.float32))
+        for i in range(W):
+            tracker.push(src[order[i]] if src is not None else None, input_ready=True)
+        tracker.flush()
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        t_host0 = time.perf_counter()
+        for i in range(W, W + K):
+            tracker.push(src[order[i]] if src is not None else None, input_ready=True)
+            if with_pose_readback:
+                tracker.pose_async(h_pose[i - W])
+        tracker.flush()                                  # the last frame's fusion belongs to the timed region
+        e1.record(stream)
+        host_ms = (time.perf_counter() - t_host0) * 1e3
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        return e0.elapsed_time(e1), host_ms
+
+    # ---- the same workload on ONE GPU (rank 0, unpartitioned): the strong-scaling reference point of this very line
+    single, single_pose, single_blocks = None, None, None
+    if rank == 0 and multi and not args.no_single:
         cfg1, _, _, _ = workload_config(name, 1, 0)
         ctx1 = Context(cfg1)
         t1 = PartitionedTracker(ctx1, 0, 1, overlap=bool(args.overlap))
+        # (timed_run uses dist.barrier when multi: the single-GPU leg runs on rank 0 alone, so it is written out here)
         t1.reset(poses[order[0]].astype(np.float32))
         for i in range(W):
             t1.push(d_frames[order[i]], input_ready=True)
+        t1.flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
@@ -451,95 +564,148 @@ def run_multi(args, rank, world, local):
         t1.flush()
         e1.record()
         torch.cuda.synchronize()
-        single = {"value": K / (e0.elapsed_time(e1) / 1e3), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / K, "n_gpus": 1}
+        st1 = ctx1.stats()
+        single_pose = t1.pose()
+        single_blocks = st1.numAllocated
+        single = {"value": K / (e0.elapsed_time(e1) / 1e3), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / K, "n_gpus": 1,
+                  "allocated_blocks": st1.numAllocated, "visible_blocks": st1.numVisible, "dropped": st1.dropped,
+                  "voxel_updates_per_s": int(st1.numUpdated) / (e0.elapsed_time(e1) / K / 1e3)}
         del t1
         ctx1.close()
-    dist.barrier()
+        torch.cuda.empty_cache()
+    if multi:
+        dist.barrier()
+
     ctx = Context(cfg)
     tracker = PartitionedTracker(ctx, rank, world, overlap=bool(args.overlap))
-    stream = torch.cuda.current_stream()
-    tracker.reset(poses[order[0]].astype(np.float32))
-    for i in range(W):
-        tracker.push(d_frames[order[i]] if rank == 0 else None, input_ready=True)
-    torch.cuda.synchronize()
-    dist.barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = tracker.launches
     with ClockSampler(local) as cs:
-        dist.barrier()                                   # the samplers start at different speeds: line the ranks up again
-        torch.cuda.synchronize()
-        ev0.record(stream)
-        upd = 0
-        t_host0 = time.perf_counter()
-        for i in range(W, W + K):
-            tracker.push(d_frames[order[i]] if rank == 0 else None, input_ready=True)
-        tracker.flush()                                  # the last frame's fusion belongs to the timed region
-        ev1.record(stream)
-        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3
-        torch.cuda.synchronize()
-    dist.barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)                        # device time, max over ranks
+        ms_local, host_enqueue_ms = timed_run(tracker, d_frames if rank == 0 else None)
+    launches = tracker.launches - l0
+
+    def allmax(x: float) -> float:
+        if not multi:
+            return float(x)
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x: float) -> float:
+        if not multi:
+            return float(x)
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    ms = allmax(ms_local)                                             # device time, max over ranks
     st = ctx.stats()
-    counts = torch.tensor([float(st.numUpdated), float(st.numVisible), float(st.numAllocated)], device="cuda")
-    dist.all_reduce(counts)
+    n_upd, n_vis, n_alloc, n_drop = allsum(st.numUpdated), allsum(st.numVisible), allsum(st.numAllocated), allsum(st.dropped)
     pose = tracker.pose()
-    # end to end: the ingest rank holds the frames in pinned HOST memory; every step copies one frame H2D, the
+    # ---- equivalence evidence carried by the line itself: pose bit-identical on every rank; equal to the 1-GPU run
+    checks = {}
+    if multi:
+        pb = torch.from_numpy(pose.astype(np.float32).view(np.int32).astype(np.int64).reshape(-1)).cuda()
+        lo, hi = pb.clone(), pb.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        checks["pose_bits_equal_across_ranks"] = bool(torch.equal(lo, hi))
+        checks["fused_peer_exchange"] = bool(tracker.fused)
+        if rank == 0 and single_pose is not None:
+            checks["max_abs_pose_minus_single_gpu"] = float(np.max(np.abs(pose - single_pose)))
+            checks["pose_within_1e-6_of_single_gpu"] = bool(checks["max_abs_pose_minus_single_gpu"] < 1e-6)
+            checks["allocated_blocks_equal_single_gpu"] = bool(int(n_alloc) == int(single_blocks))
+    # ---- end to end: the ingest rank holds the frames in pinned HOST memory; every step copies one frame H2D, the
     # frame is broadcast, and every rank reads its pose back D2H
     h_frames = torch.from_numpy(frames).pin_memory() if rank == 0 else None
     h_pose = torch.zeros((K, 16), dtype=torch.float32).pin_memory()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ev0.record(stream)
-    for i in range(W, W + K):
-        tracker.push(h_frames[order[i]] if rank == 0 else None, input_ready=True)
-        tracker.pose_async(h_pose[i - W])
+    ms_e2e_local, _ = timed_run(tracker, h_frames, with_pose_readback=True, h_pose=h_pose)
+    ms_e2e = allmax(ms_e2e_local)
+
+    # ---- per-stage device times on this rank's partition (max over ranks): `reps` back-to-back launches per stage
     tracker.flush()
-    ev1.record(stream)
     torch.cuda.synchronize()
-    ms_e2e = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-    dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    # integration alone on this rank's partition (the stage that shards): max over ranks of the device time
-    tracker.flush()
-    df = tracker.last_depthf()
-    t_int = []
-    for i in range(6):
+    stages = {}
+    maps_a, maps_b = ctx.new_maps(), ctx.new_maps()
+    d_last = tracker.depth                                           # the broadcast landing buffer of the latest frame
+    ctx.preprocess(d_last, *maps_a)
+    ctx.preprocess(tracker._depths[(tracker._pushed) & 1], *maps_b)   # the frame before it: the ICP target
+    rows = tracker.rows
+
+    def timed(fn, r=4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
         e0.record(stream)
-        ctx.integrate_depthf(df)
+        for _ in range(r):
+            fn()
         e1.record(stream)
         torch.cuda.synchronize()
-        if i >= 2:
-            t_int.append(e0.elapsed_time(e1))
-    t_int = torch.tensor([float(np.mean(t_int))], device="cuda")
-    dist.all_reduce(t_int, op=dist.ReduceOp.MAX)
-    upd = torch.tensor([float(ctx.stats().numUpdated)], device="cuda")
-    dist.all_reduce(upd)
+        return e0.elapsed_time(e1) * 1e3 / r
+
+    def align():
+        ctx.icp_reset(True)
+        ctx.icp_align_rows(maps_a[0], maps_a[1], maps_b[0], maps_b[1], rows[0], rows[1], cfg.icpIterations)
+
+    stages["preprocess"] = allmax(timed(lambda: ctx.preprocess(d_last, *maps_a)))
+    stages["icp_align"] = allmax(timed(align))
+    stages["alloc"] = allmax(timed(lambda: ctx.alloc_blocks(maps_a[0], maps_a[1])))
+    stages["compact"] = allmax(timed(lambda: ctx.compact()))
+    t_int = allmax(timed(lambda: ctx.integrate_depthf(maps_a[2])))
+    stages["integrate"] = t_int
+    st2 = ctx.stats()
+    upd_stage = allsum(st2.numUpdated)
+    n = cfg.width * cfg.height
+    peak, which = peaks()
+    # roofline of the stage that shards: per-rank algorithmic bytes / the SLOWEST rank's time
+    bytes_rank = 16 * int(st2.numUpdated) + 16 * st2.numVisible + 4 * n
+    frac_rank = bytes_rank / (t_int * 1e-6) / 1e9 / peak
+    frac_min = -allmax(-frac_rank)
+    bytes_all = allsum(bytes_rank)
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cfg1, _, _, _ = workload_config(name, 1, 0)
+        cfg1.numVoxelBlocks = min(cfg1.numVoxelBlocks, 1048576)     # host memory: 4 GiB of voxels is plenty for the 2-frame sample
+        cpu = cpu_port_baseline(cfg1, frames, poses[0], budget_s=10.0, max_frames=2)
     if rank == 0:
-        ms = float(ms.item())
         truth = poses[order[-1]]
         out = {
             "metric": METRIC, "value": K / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{name}: large-volume {cfg.width}x{cfg.height} sequence (scene S3), voxel {cfg.voxelSize} m, hash space "
-                                   f"partitioned over {world} GPUs (owner = mix(block) mod {world}), NCCL frame broadcast, 32-float ICP all-reduce "
-                                   + ("FUSED into the ICP kernel epilogue over NVLink peer memory" if tracker.fused else "through NCCL"),
-                       "l2": "per-frame voxel working set exceeds L2 on every rank",
-                       "final_pose_translation_error_m": float(np.max(np.abs(pose[:3, 3] - truth[:3, 3]))),
-                       "visible_blocks_all_ranks": int(counts[1].item()), "allocated_blocks_all_ranks": int(counts[2].item())},
-            "voxel_updates_per_s": float(counts[0].item()) / (ms / K / 1e3),
-            "integrate_stage": {"us_max_over_ranks": float(t_int.item()) * 1e3, "voxels_updated_all_ranks": int(upd.item()),
-                                "voxel_updates_per_s": float(upd.item()) / (float(t_int.item()) * 1e-3),
-                                "note": "k_integrate alone on each rank's partition of the hash space; the stage that shards"},
-            "gpu_launches": int(tracker.launches - l0),
+            "config": dict(config_dict(name, cfg, n_unique),
+                           partition=f"hash space partitioned over {world} GPU(s) (owner = mix(block) mod {world}), {cfg.numVoxelBlocks} blocks per GPU; "
+                                     "frame broadcast over NVLink (NCCL); 32-float ICP all-reduce "
+                                     + ("FUSED into the persistent Align kernel over NVLink peer memory" if tracker.fused else
+                                        ("through NCCL" if multi else "n/a (one GPU)")),
+                           l2="per-frame voxel working set exceeds L2 on every rank"),
+            "results": {"final_pose_translation_error_m": float(np.max(np.abs(pose[:3, 3] - truth[:3, 3]))),
+                        "visible_blocks_all_ranks": int(n_vis), "allocated_blocks_all_ranks": int(n_alloc), "dropped_all_ranks": int(n_drop),
+                        "voxel_working_set_MB_all_ranks": n_vis * 4096 / 1e6},
+            "checks": checks,
+            "voxel_updates_per_s": n_upd / (ms / K / 1e3),
+            "stages_us": dict(stages, note="max over ranks of each stage on the rank's own partition, CUDA events around 4 back-to-back launches; "
+                                           "in the frame loop the fusion stages of frame k run beside the tracking of frame k+1"),
+            "roofline": {"kernel": "k_integrate<Fixed,dense> (the stage that shards; per-rank partition)", "bound": "hbm",
+                         "achieved": bytes_all / (t_int * 1e-6) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_all / (t_int * 1e-6) / 1e9 / world / peak, "frac_slowest_rank": frac_min,
+                         "traffic": ncu_traffic("k_integrate"), "peak_source": which,
+                         "algorithmic_bytes_all_ranks": bytes_all, "us_max_over_ranks": t_int,
+                         "voxel_updates_per_s_all_ranks": upd_stage / (t_int * 1e-6),
+                         "note": "achieved = mean per-GPU algorithmic bytes (16 N_upd + 16 N_vis + 4 W H) / the slowest rank's launch time"},
+            "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": host_enqueue_ms / K, "clocks": cs.summary(),
             "single_gpu_same_workload": single,
-            "e2e": {"value": K / (float(ms_e2e.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(cfg.width * cfg.height * 2),
-                    "d2h_bytes_per_step": 64 * world, "ms_per_step": float(ms_e2e.item()) / K},
+            "speedup_vs_single_gpu_same_workload": (K / (ms / 1e3)) / single["value"] if single else None,
+            "e2e": {"value": K / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(cfg.width * cfg.height * 2),
+                    "d2h_bytes_per_step": 64 * world, "ms_per_step": ms_e2e / K},
         }
+        if cpu:
+            out["cpu_baseline"] = cpu
         emit(out)
-    dist.destroy_process_group()
+    if multi:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -547,8 +713,8 @@ def run_reference(args):
     """The reference arm: the reference's own CUDA kernels (rebuilt for sm_100a from /root/reference by
     oracle/Makefile, UNMODIFIED) driven with the reference's own call sequence -- SDF_Hashtable::integrate
     (4 device syncs + 2 blocking D2H per frame) and CameraTracking::Align (5 syncs + 3 D2H per iteration,
-    cuBLAS Sgemv/Ssyrk over the 7.4 MB Jacobian) -- on the frames of config C2.  Falls back to the CPU
-    transliteration when no GPU / no prebuilt oracle/_ref is available."""
+    cuBLAS Sgemv/Ssyrk over the 7.4 MB Jacobian) -- on the frames and the table geometry of config C2.  Falls back to
+    the CPU transliteration when no GPU / no prebuilt oracle/_ref is available."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -556,11 +722,11 @@ def run_reference(args):
     cfg, scene, traj, seq_len = workload_config("C2")
     n_unique = min(seq_len, max(K + W, 2))
     frames, poses = render_frames(cfg, scene, traj, n_unique)
-    cpu = cpu_port_baseline(cfg, frames, poses[0])
+    cpu = cpu_baselines(cfg, frames, poses[0])
     base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: synthetic 640x480 sequence (scene S1T, trajectory C2), reference defaults except the frames "
-                                   "(the reference has no configuration; 5000x5 buckets, 4000 blocks so the sequence fits)"}}
+            "config": config_dict("C2", cfg, n_unique),
+            "policy": "the reference's as-built arithmetic (it has no other); its kernels take the table geometry, voxel size and truncation of the config"}
     try:
         import torch
 
@@ -568,7 +734,7 @@ def run_reference(args):
 
         if not torch.cuda.is_available():
             raise RuntimeError("no GPU")
-        ref = ob.ref_lib()
+        ob.ref_lib()
     except Exception as e:  # noqa: BLE001 -- any failure means: time the CPU port instead
         out = dict(base, value=cpu["value"], ms_per_step=1e3 / cpu["value"], cpu_baseline=cpu,
                    e2e={"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -579,36 +745,52 @@ def run_reference(args):
 
     order = [pingpong(i, n_unique) for i in range(W + K)]
     n = 640 * 480
-    with silence_stdout():
-        torch.cuda.set_device(0)
-        assert ref.ref_init(5000, 5, 4000, 0.0, 0.0) == 0
-        Kc, Kinv = cfg.K(), cfg.Kinv()
-        ref.ref_set_intrinsic(Kc.ctypes.data, Kinv.ctypes.data)
-        d_frames = torch.from_numpy(frames).cuda()
-        maps = [(torch.zeros((n, 4), device="cuda"), torch.zeros((n, 4), device="cuda")) for _ in range(2)]
-        solve = ob.ref_solve_callback()
-        pose = poses[order[0]].astype(np.float64)
-        est = np.zeros(6, np.float32)
-        delta = np.eye(4, dtype=np.float32).reshape(16).copy()
-        t0 = None
-        for i, fi in enumerate(order):
-            if i == W:
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-            cur, prev = maps[i & 1], maps[1 - (i & 1)]
-            ref.ref_preprocess(cur[0].data_ptr(), cur[1].data_ptr(), d_frames[fi].data_ptr())          # Application.cpp:73
-            if i > 0:
-                ref.ref_align(cur[0].data_ptr(), prev[0].data_ptr(), prev[1].data_ptr(), 20, solve, est.ctypes.data, delta.ctypes.data)
-                pose = pose @ delta.reshape(4, 4).astype(np.float64)
-            p32 = np.ascontiguousarray(pose.astype(np.float32).reshape(16))
-            ref.ref_integrate(p32.ctypes.data, cur[0].data_ptr(), cur[1].data_ptr())                    # Application.cpp:84
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-    val = K / dt
+
+    def run_variant(variant: str, steps: int, warm: int):
+        ref = ob.ref_lib(variant)
+        with silence_stdout():
+            torch.cuda.set_device(0)
+            rc = ref.ref_init(cfg.numBuckets, cfg.bucketSize, cfg.numVoxelBlocks, cfg.voxelSize, cfg.truncation)
+            assert rc == 0, f"ref_init -> {rc}"
+            Kc, Kinv = cfg.K(), cfg.Kinv()
+            ref.ref_set_intrinsic(Kc.ctypes.data, Kinv.ctypes.data)
+            d_frames = torch.from_numpy(frames).cuda()
+            maps = [(torch.zeros((n, 4), device="cuda"), torch.zeros((n, 4), device="cuda")) for _ in range(2)]
+            solve = ob.ref_solve_callback()
+            pose = poses[order[0]].astype(np.float64)
+            est = np.zeros(6, np.float32)
+            delta = np.eye(4, dtype=np.float32).reshape(16).copy()
+            t0 = None
+            for i, fi in enumerate(order[:warm + steps]):
+                if i == warm:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                cur, prev = maps[i & 1], maps[1 - (i & 1)]
+                ref.ref_preprocess(cur[0].data_ptr(), cur[1].data_ptr(), d_frames[fi].data_ptr())          # Application.cpp:73
+                if i > 0:
+                    ref.ref_align(cur[0].data_ptr(), prev[0].data_ptr(), prev[1].data_ptr(), 20, solve, est.ctypes.data, delta.ctypes.data)
+                    pose = pose @ delta.reshape(4, 4).astype(np.float64)
+                p32 = np.ascontiguousarray(pose.astype(np.float32).reshape(16))
+                ref.ref_integrate(p32.ctypes.data, cur[0].data_ptr(), cur[1].data_ptr())                    # Application.cpp:84
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        return steps / dt, dt
+
+    val, dt = run_variant("", K, W)
+    variants = {}
+    for v, label in (("noprintf", "device printf calls of insertVoxelEntry (VoxelUtils.cu:433-435, :452) deleted"),
+                     ("G", "the shipped flags: -G device debug build (CMakeLists.txt:21)")):
+        try:
+            steps_v = K if v == "noprintf" else max(3, min(K, 6))
+            vv, _ = run_variant(v, steps_v, min(W, 3))
+            variants[v] = {"value": vv, "unit": UNIT, "steps": steps_v, "what": label}
+        except Exception as e:  # noqa: BLE001
+            variants[v] = {"unavailable": str(e)}
     out = dict(base, value=val, ms_per_step=1e3 * dt / K,
                cpu_baseline={"value": val, "unit": UNIT, "cores": 0, "kind": "reference",
                              "sample": f"{K} frames after {W} warm-up; the reference's OWN CUDA kernels rebuilt for sm_100a "
                                        "(-O3 -fmad=false, no -G), its own host syncs and device printf left in; it has no CPU path"},
+               variants=variants,
                cpu_port=cpu,
                e2e={"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
     emit(out)
@@ -621,10 +803,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "C2", "C3", "C4", "C5"],
-                    help="C2 (default at N=1), C3 (720p, 5 mm), C4 (large volume; default at N>1), C5 (C2 tracked frame-to-model: raycast in the loop)")
+                    help="C2 (default at N=1), C3 (720p, 5 mm), C4 (2 mm large volume; default at N>1 and under torchrun), "
+                         "C5 (C2 tracked frame-to-model: raycast in the loop)")
     ap.add_argument("--overlap", type=int, default=1, help="1: fuse frame k beside the tracking of frame k+1 (VH_PIPE_OVERLAP); 0: strictly serial frames")
+    ap.add_argument("--repeats", type=int, default=5, help="N=1: how many times the W warm-up + K timed steps pass is repeated (median reported)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm", action="store_true", help="skip the large-volume integrate roofline leg")
+    ap.add_argument("--no-refexact", action="store_true", help="skip the RefExact leg of the repo's own kernels")
     ap.add_argument("--no-single", action="store_true", help="multi-GPU: skip the 1-GPU run of the same workload")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -380,17 +380,19 @@ def block_in_frustum(cfg, pose, x, y, z) -> bool:
 
 
 # ---- reference CUDA harness (GPU box only) --------------------------------------------------------------
-_rlib = None
+_rlib = {}
 
 
-def ref_lib() -> C.CDLL:
-    """oracle/_ref/libvh_ref.so: the reference's own .cu files + ref_harness.cu. Needs a GPU to run."""
-    global _rlib
-    if _rlib is not None:
-        return _rlib
-    if not REF_LIB.exists():
-        raise FileNotFoundError(f"{REF_LIB} not built (make -C oracle ref; needs /root/reference)")
-    lib = C.CDLL(str(REF_LIB), mode=C.RTLD_LOCAL)
+def ref_lib(variant: str = "") -> C.CDLL:
+    """oracle/_ref/libvh_ref[_<variant>].so: the reference's own .cu files + ref_harness.cu. Needs a GPU to run.
+    variant "" = -O3 as BASELINE.md 3.1 states; "noprintf" = the two device printf calls of insertVoxelEntry deleted;
+    "G" = the shipped -G (device debug) flags.  One variant per process: they share the reference's global symbols."""
+    if variant in _rlib:
+        return _rlib[variant]
+    path = REF_LIB if not variant else REF_LIB.with_name(f"libvh_ref_{variant}.so")
+    if not path.exists():
+        raise FileNotFoundError(f"{path} not built (make -C oracle ref; needs /root/reference)")
+    lib = C.CDLL(str(path), mode=C.RTLD_LOCAL)
     P, I, F = C.c_void_p, C.c_int, C.c_float
     lib.ref_init.argtypes = [I, I, I, F, F]
     lib.ref_init.restype = I
@@ -421,7 +423,7 @@ def ref_lib() -> C.CDLL:
     lib.ref_build_system.restype = None
     lib.ref_align.argtypes = [P, P, P, I, P, P, P]
     lib.ref_align.restype = I
-    _rlib = lib
+    _rlib[variant] = lib
     return lib
 
 

@@ -13,6 +13,7 @@ import pytest
 from conftest import entries_to_set, render, rot_err, small_cfg
 
 pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
 
 torch = pytest.importorskip("torch")
 
@@ -399,6 +400,125 @@ def test_track_frame_is_preprocess_plus_align_plus_pose_chain(built_library, ora
         b.track_frame(cu(d1.reshape(-1)), v2, n2, f2, tv, tn, 12, p_in, p_in)
         torch.cuda.synchronize()
         assert np.array_equal(bits(p_in.cpu().numpy().reshape(4, 4)), bits(want))
+
+
+def test_host_classes_solver_and_camera_tracking(built_library, oracle, tmp_path):
+    """SURVEY row a23: Solver::BuildLinearSystem and CameraTracking::Align are EXECUTED through the C++ classes (a test
+    harness written like the reference's own host loop, tests/cpp/host_classes_driver.cpp) and pinned to the oracle."""
+    import subprocess
+
+    exe = tmp_path / "host_classes_driver"
+    lib_dir = Path(built_library).parent
+    r = subprocess.run(["g++", "-std=c++17", "-O1", str(ROOT / "tests/cpp/host_classes_driver.cpp"), "-I", str(ROOT / "include"),
+                        "-I", "/usr/local/cuda/include", "-L", str(lib_dir), "-lvh_b200", "-L", "/usr/local/cuda/lib64", "-lcudart",
+                        f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cfg = Config(policy=POLICY_REF_EXACT)
+    T0, T1 = scenes.trajectory_C2(0), scenes.trajectory_C2(12)
+    d0, d1 = render(cfg, scenes.scene_S1T(), T0), render(cfg, scenes.scene_S1T(), T1)
+    np.concatenate([d0.reshape(-1), d1.reshape(-1)]).astype(np.uint16).tofile(tmp_path / "in.bin")
+    r = subprocess.run([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
+    facade, loop, ldlt = (out[k * 16:(k + 1) * 16].reshape(4, 4) for k in range(3))
+    back, JTJ, JTr = out[48:54], out[54:90].reshape(6, 6).astype(np.float64), out[90:96].astype(np.float64)
+    ot = oracle.OracleTable(cfg)
+    tv, tn, _ = ot.preprocess(d0)
+    iv, inn, _ = ot.preprocess(d1)
+    its, oest, odelta = oracle.icp_align(cfg, iv, inn, tv, tn, 20)
+    for got in (facade, loop):                              # both routes: the oracle's 20-iteration pose within 1e-4
+        assert rot_err(got[:3, :3], odelta[:3, :3]) <= 1e-4
+        assert np.max(np.abs(got[:3, 3] - odelta[:3, 3])) <= 1e-4
+    assert np.max(np.abs(facade - loop)) <= 2e-5           # fused association vs stored correspondences: summation order only
+    # host LDLT (Solver::SolveJacobianSystem) against an fp64 solve + matrix exponential of that very system
+    from scipy.linalg import expm
+    x = -np.linalg.solve(JTJ, JTr)
+    Xi = np.zeros((4, 4))
+    Xi[:3, :3] = [[0, -x[5], x[4]], [x[5], 0, -x[3]], [-x[4], x[3], 0]]
+    Xi[:3, 3] = x[:3]
+    assert np.max(np.abs(ldlt - expm(Xi))) <= 1e-6
+    assert np.max(np.abs(back - np.array([0.02, -0.01, 0.03, 0.04, -0.02, 0.01], np.float32))) <= 1e-6
+
+
+def _system32(JtJ, Jtr, count=1e5, err=1.0):
+    s = np.zeros(32, np.float32)
+    k = 0
+    for i in range(6):
+        for j in range(i, 6):
+            s[k] = JtJ[i, j]
+            k += 1
+    s[21:27] = Jtr
+    s[27], s[28] = err, count
+    return s
+
+
+@pytest.mark.parametrize("policy", [POLICY_REF_EXACT, POLICY_FIXED])
+def test_device_solve_against_fp64_on_conditioned_and_degenerate_systems(built_library, oracle, policy):
+    """The on-device 6x6 solve + SE(3) update (fp32 LDL^T without pivoting, closed-form exponential; replaces Eigen's
+    inverse() / exp() / log(), ref Solver.cpp:91-111, SE3.cpp:4-19 -- the parity-UNPINNED half of a23) against an fp64
+    numpy solve + scipy expm: well-conditioned, badly scaled (cond 1e6), and rank-deficient (a planar scene) systems."""
+    from scipy.linalg import expm
+
+    ctx = Context(Config(policy=policy, numBuckets=64, numVoxelBlocks=64))
+    rng = np.random.default_rng(7)
+
+    def run(JtJ, Jtr, start=None):
+        ctx.icp_reset(True)
+        if start is not None:
+            ctx.icp_set_twist(start)
+        before = ctx.icp_get()[0].astype(np.float64)
+        ctx.icp_solve(cu(_system32(JtJ, Jtr)))
+        torch.cuda.synchronize()
+        return before, ctx.icp_get()[0].astype(np.float64)
+
+    def want(JtJ, Jtr, before):
+        x = -np.linalg.solve(JtJ.astype(np.float64), Jtr.astype(np.float64))
+        Xi = np.zeros((4, 4))
+        Xi[:3, :3] = [[0, -x[5], x[4]], [x[5], 0, -x[3]], [-x[4], x[3], 0]]
+        Xi[:3, 3] = x[:3]
+        return expm(Xi) @ before, x
+
+    # (1) the normal equations of a real frame pair: rows (n, p x n) of a sphere + plane scene
+    for trial in range(4):
+        P = rng.uniform(-1, 1, (4000, 3)) + np.array([0, 0, 2.5])
+        Nn = rng.normal(size=(4000, 3))
+        Nn /= np.linalg.norm(Nn, axis=1, keepdims=True)
+        J = np.concatenate([Nn, np.cross(P, Nn)], axis=1)
+        r = rng.normal(scale=0.01, size=4000)
+        JtJ, Jtr = (J.T @ J).astype(np.float32), (J.T @ r).astype(np.float32)
+        start = np.array([0.03, -0.02, 0.01, 0.02, 0.01, -0.03], np.float32) if trial % 2 else None
+        before, got = run(JtJ, Jtr, start)
+        exp_, x = want(JtJ, Jtr, before)
+        cond = np.linalg.cond(JtJ.astype(np.float64))
+        assert np.max(np.abs(got - exp_)) <= 2e-6 + 4e-7 * cond * np.max(np.abs(x)), (trial, cond)
+        assert np.max(np.abs(got[:3, :3].T @ got[:3, :3] - np.eye(3))) <= 1e-6       # re-orthonormalised
+    # (2) badly scaled but full rank (cond ~ 1e6): the error grows with the condition number, not beyond it
+    Q, _ = np.linalg.qr(rng.normal(size=(6, 6)))
+    JtJ = (Q @ np.diag([1e6, 3e5, 1e4, 1e3, 30.0, 1.0]) @ Q.T)
+    JtJ = ((JtJ + JtJ.T) / 2).astype(np.float32)
+    Jtr = (JtJ.astype(np.float64) @ np.array([1e-3, -2e-3, 1e-3, 2e-3, -1e-3, 1e-3])).astype(np.float32)
+    before, got = run(JtJ, Jtr)
+    exp_, x = want(JtJ, Jtr, before)
+    assert np.all(np.isfinite(got))
+    assert np.max(np.abs(got - exp_)) <= 1e-6 * np.linalg.cond(JtJ.astype(np.float64)) * 1e-3 + 1e-5
+    # (3) rank-deficient: a single plane constrains 3 of the 6 degrees of freedom (exactly representable rows, so the
+    # elimination meets an exact zero pivot).  The solve must refuse -- state unchanged, iteration stopped -- not return garbage.
+    Pp = np.stack([rng.integers(-8, 8, 64), rng.integers(-8, 8, 64), np.full(64, 2)], axis=1).astype(np.float64)
+    Np = np.tile([0.0, 0.0, 1.0], (64, 1))
+    J = np.concatenate([Np, np.cross(Pp, Np)], axis=1)
+    JtJ, Jtr = (J.T @ J).astype(np.float32), (J.T @ np.full(64, 0.25)).astype(np.float32)
+    assert np.linalg.matrix_rank(JtJ.astype(np.float64)) == 3
+    before, got = run(JtJ, Jtr, np.array([0.01, 0.02, -0.01, 0.01, -0.02, 0.02], np.float32))
+    assert np.array_equal(before, got), "a singular system changed the pose"
+    # and the whole Align stops cleanly on such a scene (a fronto-parallel wall): finite pose, no iteration counted past the failure
+    cfgp = Config(policy=policy)
+    wall = np.full((cfgp.height, cfgp.width), 10000, np.uint16)
+    c2 = Context(cfgp)
+    v, n, _ = gpu_preprocess(c2, wall)
+    c2.icp_reset(True)
+    c2.icp_align(v, n, v, n, 20)
+    d = c2.icp_get()[0]
+    assert np.all(np.isfinite(d))
 
 
 def test_linear_system_300_contract(built_library, oracle):

@@ -17,7 +17,7 @@ what = sys.argv[1] if len(sys.argv) > 1 else "integrate"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 
 if what == "integrate":          # large-volume integrate: working set > 2x L2
-    cfg, scene, traj, _ = bench.workload_config("C4")
+    cfg, scene, traj, _ = bench.workload_config("C4_4mm")
     ctx = Context(cfg)
     pose = traj(0).astype(np.float32)
     d = torch.from_numpy(scenes.render_depth(scene, pose, cfg.width, cfg.height, cfg.fx, cfg.fy, cfg.cx, cfg.cy).reshape(-1)).cuda()
