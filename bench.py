@@ -214,10 +214,8 @@ def cpu_port_baseline(cfg, frames, pose0, budget_s=12.0, max_frames=40, threads=
     from oracle import binding as ob
 
     lib = ob.oracle_lib()
-    all_cores = lib.vo_num_threads() if not threads else None
-    if threads:
-        all_cores = lib.vo_num_threads()
-        lib.vo_set_num_threads(threads)
+    all_cores = os.cpu_count() or lib.vo_num_threads()      # torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly
+    lib.vo_set_num_threads(threads if threads else all_cores)
     cores = lib.vo_num_threads()
     ot = ob.OracleTable(cfg)
     pose = pose0.astype(np.float32)
@@ -236,8 +234,7 @@ def cpu_port_baseline(cfg, frames, pose0, budget_s=12.0, max_frames=40, threads=
             break
     dt = time.perf_counter() - t0
     ot.close()
-    if threads and all_cores:
-        lib.vo_set_num_threads(all_cores)
+    lib.vo_set_num_threads(all_cores)
     return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {done} frames of the workload ({dt:.1f} s): oracle/ C++ port, OpenMP x{cores}, "
                       f"preprocess + {cfg.icpIterations}-iteration Align + alloc + compact + integrate per frame"}

@@ -6,6 +6,7 @@ ICP normal equations relative 1e-5; pose within 1e-4 in rotation and translation
 """
 import ctypes as C
 import os
+from pathlib import Path
 
 import numpy as np
 import pytest
