@@ -610,7 +610,9 @@ def run_partitioned(args, rank, world, local):
         if rank == 0 and single_pose is not None:
             checks["max_abs_pose_minus_single_gpu"] = float(np.max(np.abs(pose - single_pose)))
             checks["pose_within_1e-6_of_single_gpu"] = bool(checks["max_abs_pose_minus_single_gpu"] < 1e-6)
-            checks["allocated_blocks_equal_single_gpu"] = bool(int(n_alloc) == int(single_blocks))
+            # a pose that differs in its last bits can move a band end point across a block face: a handful of blocks may differ
+            checks["allocated_blocks_minus_single_gpu"] = int(n_alloc) - int(single_blocks)
+            checks["allocated_blocks_within_1e-5_of_single_gpu"] = bool(abs(int(n_alloc) - int(single_blocks)) <= 1e-5 * int(single_blocks))
     # ---- end to end: the ingest rank holds the frames in pinned HOST memory; every step copies one frame H2D, the
     # frame is broadcast, and every rank reads its pose back D2H
     h_frames = torch.from_numpy(frames).pin_memory() if rank == 0 else None

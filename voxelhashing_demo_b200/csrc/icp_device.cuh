@@ -383,6 +383,9 @@ __device__ __forceinline__ unsigned long long llLoadSys(const unsigned long long
 __device__ __forceinline__ bool llReady(unsigned long long w, unsigned seq) { return (unsigned)(w >> 32) == seq; }
 __device__ __forceinline__ float llValue(unsigned long long w) { return __uint_as_float((unsigned)w); }
 
+#ifndef VH_PEER_BACKOFF
+#define VH_PEER_BACKOFF 0
+#endif
 // ---- fused cross-GPU all-reduce (one process per GPU, peer memory over NVLink / NVSwitch) --------------
 // Executed by one warp: lane L holds value L of this rank's 32-float system.  Scatter it into every rank's
 // exchange region (P2P stores over NVLink), wait for all ranks' contributions, add them in RANK ORDER (so every
@@ -405,7 +408,12 @@ __device__ __forceinline__ float peerGather(const PeerView& pv, unsigned seq) {
 #pragma unroll
     for (int r = 0; r < kMaxPeers; ++r) {
         if (r >= pv.world) break;
-        while (!llReady(w[r], seq)) w[r] = llLoadSys(peerWord(pv, pv.rank, seq & 1u, r, lane));
+        while (!llReady(w[r], seq)) {
+#if VH_PEER_BACKOFF > 0
+            __nanosleep(VH_PEER_BACKOFF);                    // the mailbox lines are the target of the peers' NVLink stores
+#endif
+            w[r] = llLoadSys(peerWord(pv, pv.rank, seq & 1u, r, lane));
+        }
         t += llValue(w[r]);
     }
     return t;
