@@ -290,6 +290,11 @@ def run_own(args):
     stream = torch.cuda.Stream()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+    def push_dev(pipe, frame):
+        # the frames are resident in HBM and nothing on `stream` produces them: the "ready" entry point lets the pipeline
+        # pre-process frame k+1 beside the Align of frame k (--ready 0: vh_pipeline_push_device, ordered behind the stream)
+        return pipe.push_device_ready(frame, None, stream) if args.ready else pipe.push_device(frame, stream)
+
     def sequence_runner(ctx, cfg_):
         def run_sequence(host: bool, sample_clocks: bool = False):
             ctx.reset(stream)
@@ -298,7 +303,7 @@ def run_own(args):
             with torch.cuda.stream(stream):
                 pipe.reset(poses[order[0]].astype(np.float32), stream)
                 for i in range(W):
-                    (pipe.push_host(h_frames[order[i]], h_pose[i], stream) if host else pipe.push_device(d_frames[order[i]], stream))
+                    (pipe.push_host(h_frames[order[i]], h_pose[i], stream) if host else push_dev(pipe, d_frames[order[i]]))
                 pipe.flush(stream)
                 stream.synchronize()
                 l0 = pipe.launches()
@@ -306,7 +311,7 @@ def run_own(args):
                     torch.cuda.synchronize()
                     ev0.record(stream)
                     for i in range(W, W + K):
-                        (pipe.push_host(h_frames[order[i]], h_pose[i], stream) if host else pipe.push_device(d_frames[order[i]], stream))
+                        (pipe.push_host(h_frames[order[i]], h_pose[i], stream) if host else push_dev(pipe, d_frames[order[i]]))
                     pipe.flush(stream)                      # overlapped schedule: the last frame's fusion belongs to the timed region
                     ev1.record(stream)
                     stream.synchronize()
@@ -805,6 +810,7 @@ def main():
                     help="C2 (default at N=1), C3 (720p, 5 mm), C4 (2 mm large volume; default at N>1 and under torchrun), "
                          "C5 (C2 tracked frame-to-model: raycast in the loop)")
     ap.add_argument("--overlap", type=int, default=1, help="1: fuse frame k beside the tracking of frame k+1 (VH_PIPE_OVERLAP); 0: strictly serial frames")
+    ap.add_argument("--ready", type=int, default=0, help="N=1 device-resident leg: 1 = vh_pipeline_push_device_ready (input complete, no producer on the stream), 0 = vh_pipeline_push_device")
     ap.add_argument("--repeats", type=int, default=5, help="N=1: how many times the W warm-up + K timed steps pass is repeated (median reported)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm", action="store_true", help="skip the large-volume integrate roofline leg")

@@ -169,6 +169,11 @@ int  vh_set_intrinsics(vh_context* ctx, float fx, float fy, float cx, float cy);
 /* SetCameraIntrinsic semantics on a context: K and K^-1 used verbatim (9 floats each, row-major). */
 int  vh_set_intrinsic_matrices(vh_context* ctx, const float* K9, const float* Kinv9);
 unsigned long long vh_bytes_allocated(vh_context* ctx);
+/* Scheduling knobs of the overlapped frame loop: CTAs of the persistent Align kernel (one per SM; default: all SMs but
+ * 8) and the number of SMs the persistent integrate grid leaves free.  The two grids cannot share an SM, so tracking(k+1)
+ * and fusion(k) run side by side only if each leaves the other whole SMs (large volumes on a partitioned context: a
+ * small Align grid + the same number of reserved SMs).  <= 0 / < 0 keep the current value. */
+int vh_set_tuning(vh_context* ctx, int align_ctas, int fusion_reserved_sms);
 
 /* ---- pre-processing (ref CameraTrackingUtils.cu:50-120) ------------------------------ */
 /* depth (u16, W*H) -> verts, normals (float4, W*H); depthf (float metres, W*H) optional. */
@@ -344,6 +349,11 @@ void vh_pipeline_destroy(vh_pipeline* p);
 int  vh_pipeline_reset(vh_pipeline* p, const float* pose_rowmajor_host, vh_stream s);
 /* One frame, depth already in device memory. Returns after enqueueing. */
 int  vh_pipeline_push_device(vh_pipeline* p, const uint16_t* d_depth, vh_stream s);
+/* Same, for a depth image that is NOT produced by work on stream s: it is complete in device memory once `ready_event`
+ * (a cudaEvent_t; NULL = complete already) has fired.  With VH_PIPE_OVERLAP the pre-processing of the frame then runs
+ * BESIDE the tracking of the previous frame instead of behind it (the per-frame tracking chain is the Align kernel
+ * alone).  The buffer must stay untouched until s -- which is ordered behind the frame's pose -- gets there. */
+int  vh_pipeline_push_device_ready(vh_pipeline* p, const uint16_t* d_depth, void* ready_event, vh_stream s);
 /* One frame end to end: H2D of the (pinned) host depth, the frame, D2H of the pose into
  * h_pose_out (pinned, 16 floats, may be NULL). Returns after enqueueing; sync the stream to read. */
 int  vh_pipeline_push_host(vh_pipeline* p, const uint16_t* h_depth, float* h_pose_out, vh_stream s);

@@ -652,7 +652,10 @@ def test_pipeline_tracks_synthetic_trajectory(built_library, oracle):
     frames = [cu(render(cfg, scenes.scene_S1T(), p).reshape(-1)) for p in poses]
     results = []
     models = []
-    for use_graph, overlap, fused_pre in ((True, False, False), (False, False, False), (True, True, False), (True, True, True)):
+    # graph replay / plain launches / overlapped schedule (input produced on the stream; input ready: its pre-processing runs
+    # beside the previous Align) / pre-processing fused into the Align kernel
+    for use_graph, overlap, fused_pre, ready in ((True, False, False, False), (False, False, False, False), (True, True, False, False),
+                                                 (True, True, True, False), (True, True, False, True)):
         os.environ["VH_PIPE_FUSED_PRE"] = "1" if fused_pre else "0"      # read at pipeline creation
         ctx = Context(cfg)
         pipe = FramePipeline(ctx, iterations=10, mode=FramePipeline.FRAME_TO_FRAME, use_graph=use_graph, overlap=overlap)
@@ -660,7 +663,7 @@ def test_pipeline_tracks_synthetic_trajectory(built_library, oracle):
         with torch.cuda.stream(s):
             pipe.reset(poses[0].astype(np.float32))
             for f in frames:
-                pipe.push_device(f)
+                pipe.push_device_ready(f, None) if ready else pipe.push_device(f)
             pose = pipe.pose()
             st = ctx.stats(s)
         results.append((pose, st.numAllocated, int(st.numUpdated), pipe.launches()))
@@ -673,7 +676,7 @@ def test_pipeline_tracks_synthetic_trajectory(built_library, oracle):
         assert np.array_equal(bits(results[0][0]), bits(r[0]))
         assert results[0][1:3] == r[1:3]
     # kernels per frame: preprocess, Align, frame constants, alloc + compact + integrate
-    assert results[0][3] == results[1][3] == results[2][3] == 40 + 39 + 40 + 40 * 3
+    assert results[0][3] == results[1][3] == results[2][3] == results[4][3] == 40 + 39 + 40 + 40 * 3
     assert results[3][3] == 1 + 39 + 40 + 40 * 3              # pre-processing of the tracked frames inside the Align kernel
     os.environ.pop("VH_PIPE_FUSED_PRE", None)
     for m in models[1:]:

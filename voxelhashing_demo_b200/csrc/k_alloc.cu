@@ -186,6 +186,7 @@ template <class P, int SRC>
 __global__ void __launch_bounds__(256) k_alloc(View v, const void* __restrict__ src) {
     __shared__ unsigned long long filter[kFilterSize];
     __shared__ float sPose[16];
+    VH_TL(TL_ALLOC, 0);
     for (int i = threadIdx.x; i < kFilterSize; i += 256) filter[i] = kFilterEmpty;
     if (threadIdx.x < 16) sPose[threadIdx.x] = v.frame->pose[threadIdx.x];
     __syncthreads();

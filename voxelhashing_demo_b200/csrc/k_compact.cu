@@ -14,6 +14,7 @@ namespace vh {
 template <class P>
 __global__ void __launch_bounds__(256) k_compact(View v) {
     __shared__ float sM[16];
+    VH_TL(TL_COMPACT, 0);
     if (threadIdx.x < 16) sM[threadIdx.x] = P::fixed ? v.frame->inv[threadIdx.x] : v.frame->pose[threadIdx.x];
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;

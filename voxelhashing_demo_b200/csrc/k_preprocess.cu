@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256) k_preprocess(View v, const uint16_t* __re
                                                     float4* __restrict__ normals, float* __restrict__ depthf) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    VH_TL(TL_PREPROCESS, 0);
     if (x >= v.W || y >= v.H) return;
     preprocessPixel<P, SMOOTH>(v, depth, x, y, verts, normals, depthf);
 }

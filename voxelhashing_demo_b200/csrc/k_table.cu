@@ -57,6 +57,7 @@ typedef Pose16f Pose16;
 //      = d_pose * d_delta             (camera->world chain: T_k = T_{k-1} * delta)
 __global__ void k_set_frame(View v, FrameParams* frame, Pose16 hostPose, const float* d_pose, const float* d_delta,
                             float* d_poseOut) {
+    VH_TL(TL_SET_FRAME, 0);
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float p[16];
     if (d_pose == nullptr) {
@@ -84,6 +85,7 @@ __global__ void k_set_frame(View v, FrameParams* frame, Pose16 hostPose, const f
     v.ctr->compactCount = 0;     // ref flattenIntoBuffer: cudaMemset(counter, 0), VoxelUtils.cu:760
     v.ctr->numUpdated = 0ull;
     v.ctr->lastInserted = 0;
+    VH_TL(TL_SET_FRAME, 1);
 }
 
 __global__ void k_reset_mutex(View v) {   // ref resetHashTableMutexes, VoxelUtils.cu:146-149
@@ -153,3 +155,16 @@ cudaError_t launch_export_entries(vh_context* c, VoxelEntry* d_out, int* d_count
 }
 
 }  // namespace vh
+
+#ifdef VH_TIMELINE
+extern "C" int vh_timeline_read(vh_context* c, unsigned long long* host, int cap, int reset) {
+    if (!c || !c->v.tl) return -1;
+    unsigned long long n = 0;
+    cudaMemcpy(&n, c->v.tl, sizeof(n), cudaMemcpyDeviceToHost);
+    if (n > vh::kTimelineCap) n = vh::kTimelineCap;
+    if ((long long)n > cap) n = (unsigned long long)cap;
+    cudaMemcpy(host, c->v.tl + 1, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(c->v.tl, 0, sizeof(unsigned long long));
+    return (int)n;
+}
+#endif

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
 
     // every CTA reads the sequence base before any CTA can finish (the base is only rewritten by CTA 0 after the last
     // exchange, which needs every CTA's contribution)
+    VH_TL(TL_ALIGN, 0);
     unsigned seq = __ldcg(&v.ctr->icpSeq);
     const unsigned seq0 = seq;
     if (threadIdx.x < 16) sDelta[threadIdx.x] = __ldcg(st->delta + threadIdx.x);
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(kIcpThreads, 1) k_icp_align(View v, IcpState* 
             v.ctr->icpSeq = seq;
         }
     }
+    VH_TL(TL_ALIGN, 1);
 }
 
 #ifdef VH_ICP_TRACE

@@ -180,6 +180,13 @@ int vh_create(const vh_config* cfg, vh_context** out) {
     // beside the tracking of this one (r2: 140 of 148 CTAs -> +7 % frames/s at VGA, Align itself +0.7 %)
     c->icpCtas = c->numSMs > 32 ? c->numSMs - 8 : c->numSMs;
     if (const char* env = getenv("VH_ICP_CTAS")) c->icpCtas = atoi(env);
+    if (const char* env = getenv("VH_FUSION_RESERVE_SMS")) c->fusionReserveSMs = atoi(env);
+#ifdef VH_TIMELINE
+    if (const char* env = getenv("VH_TIMELINE")) if (env[0] == '1') {
+        chk(devAlloc(c, &v.tl, (size_t)kTimelineCap + 1));
+        if (e == cudaSuccess) chk(cudaMemset(v.tl, 0, sizeof(unsigned long long) * (kTimelineCap + 1)));
+    }
+#endif
     {
         const size_t tiles = (size_t)((cfg->width + 7) / 8) * ((cfg->height + 7) / 8);
         chk(devAlloc(c, &c->tileMin, tiles));
@@ -202,7 +209,7 @@ void vh_destroy(vh_context* c) {
     if (!c) return;
     cudaFree(c->v.entries); cudaFree(c->v.chain); cudaFree(c->v.mutex); cudaFree(c->v.heap);
     cudaFree(c->v.blockInfo); cudaFree(c->v.voxels); cudaFree(c->v.compact16); cudaFree(c->v.compact20);
-    cudaFree(const_cast<float*>(c->v.bilatLut)); cudaFree(c->v.depthSmooth);
+    cudaFree(const_cast<float*>(c->v.bilatLut)); cudaFree(c->v.depthSmooth); cudaFree(c->v.tl);
     cudaFree(c->v.ctr); cudaFree(c->frame); cudaFree(c->icp); cudaFree(c->icpPartials); cudaFree(c->icpLL); cudaFree(c->tileMin); cudaFree(c->tileMax);
     delete c;
 }
@@ -219,6 +226,17 @@ int vh_reset(vh_context* c, vh_stream s) {
 int vh_get_config(const vh_context* c, vh_config* out) {
     if (!c || !out) return fail(VH_ERR_INVALID, "vh_get_config: null argument");
     *out = c->cfg;
+    return VH_OK;
+}
+
+// Scheduling knobs of the overlapped frame loop (vh_pipeline, VH_PIPE_OVERLAP): the Align grid (one 512-thread CTA per
+// SM, the whole register file of each) and the persistent integrate grid cannot share an SM, so they overlap only if each
+// leaves the other whole SMs.  align_ctas <= 0 / fusion_reserved_sms < 0 keep the current value.
+int vh_set_tuning(vh_context* c, int align_ctas, int fusion_reserved_sms) {
+    if (!c) return fail(VH_ERR_INVALID, "vh_set_tuning: null context");
+    if (align_ctas > c->numSMs || fusion_reserved_sms >= c->numSMs) return fail(VH_ERR_INVALID, "vh_set_tuning: more SMs than the device has");
+    if (align_ctas > 0) c->icpCtas = align_ctas;
+    if (fusion_reserved_sms >= 0) c->fusionReserveSMs = fusion_reserved_sms;
     return VH_OK;
 }
 

@@ -190,6 +190,24 @@ __device__ __forceinline__ float warpSum(float x) {
     return x;
 }
 
+// ---- optional kernel timeline (build with -DVH_TIMELINE; tools/timeline.py): CTA 0 of every kernel of the frame loop
+// appends {kernel id, begin / end, %globaltimer} to a global log, so the interleaving of the streams can be READ
+// instead of guessed.
+#ifdef VH_TIMELINE
+__device__ __forceinline__ void tlStamp(const View& v, int kernel, int phase) {
+    if (v.tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned long long i = atomicAdd(v.tl, 1ull);           // word 0 = count, then the log
+        if (i < kTimelineCap) v.tl[1 + i] = (t << 8) | ((unsigned long long)kernel << 1) | (unsigned long long)phase;
+    }
+}
+#define VH_TL(kernel, phase) tlStamp(v, kernel, phase)
+#else
+#define VH_TL(kernel, phase)
+#endif
+enum { TL_PREPROCESS = 1, TL_ALIGN = 2, TL_SET_FRAME = 3, TL_ALLOC = 4, TL_COMPACT = 5, TL_INTEGRATE = 6 };
+
 }  // namespace vh
 
 #endif

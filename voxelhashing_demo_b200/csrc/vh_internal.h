@@ -82,11 +82,13 @@ struct View {
     float bilatG[3];
     const float* bilatLut;           // kBilatLut entries, nullptr = filter off
     float* depthSmooth;              // W x H filtered depth, raw units as float
+    unsigned long long* tl;          // kernel timeline log (builds with -DVH_TIMELINE and VH_TIMELINE=1 in the environment), else nullptr
 };
 
 constexpr int kIcpMaxBlocks = 1024;
 // exchange rows of the persistent Align kernel (k_track.cu): 2 parities x (one row per CTA + one row per group of 16 CTAs) x 32 words
 constexpr size_t kIcpLLWords = (size_t)2 * kIcpMaxBlocks * 32 + (size_t)2 * (kIcpMaxBlocks / 16) * 32;
+constexpr unsigned long long kTimelineCap = 1ull << 16;
 constexpr int kBilatLut = 1024;      // |delta depth| >= this many raw units contributes nothing
 
 // Fused all-reduce of the ICP normal equations over NVLink peer memory.
@@ -109,6 +111,7 @@ struct vh_context {
     float* icpPartials;       // kIcpMaxBlocks x 32
     unsigned long long* icpLL;   // persistent Align (k_track.cu): 2 x kIcpMaxBlocks x 32 {value, sequence} words
     int icpCtas;              // CTAs of the persistent Align kernel (0 = one per SM); VH_ICP_CTAS / vh_set_tuning
+    int fusionReserveSMs;     // SMs the persistent fusion kernels leave free (for a co-resident Align grid); VH_FUSION_RESERVE_SMS / vh_set_tuning
     int* tileMin;             // raycast ray intervals, (W/8) x (H/8), float bit patterns
     int* tileMax;
     int numSMs;

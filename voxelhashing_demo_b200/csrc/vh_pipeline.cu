@@ -25,6 +25,8 @@
 
 using namespace vh;
 
+constexpr int kMapSets = 3;
+
 struct vh_pipeline {
     vh_context* ctx;
     int iterations;
@@ -39,25 +41,28 @@ struct vh_pipeline {
     cudaStream_t copyStream;       // H2D of frame k+1 overlaps the compute of frame k
     cudaEvent_t evCopied[2], evConsumed[2];
     long long hostFrames;
-    float4* verts[2];
-    float4* normals[2];
-    float* depthf[2];
+    // THREE map sets, used round robin (frame k -> set k % 3): the maps of frame k are the source of Align(k), the target
+    // of Align(k+1) and the input of fusion(k); with two sets the pre-processing of frame k+2 had to wait for fusion(k) --
+    // which runs beside Align(k+1) and finishes after it (r2 timeline: 13 us per frame at VGA, the whole integrate at 2 mm)
+    float4* verts[kMapSets];
+    float4* normals[kMapSets];
+    float* depthf[kMapSets];
     float4* modelVerts;            // raycast maps (frame-to-model)
     float4* modelNormals;
-    cudaGraph_t graph[2];
-    cudaGraphExec_t exec[2];
-    bool haveGraph[2];
+    cudaGraph_t graph[kMapSets];
+    cudaGraphExec_t exec[kMapSets];
+    bool haveGraph[kMapSets];
     // overlapped schedule (VH_PIPE_OVERLAP): fusion of frame k runs on its own stream beside preprocess + ICP of frame k+1
     bool overlap;
     bool fusedPre;                 // VH_PIPE_FUSED_PRE=1: pre-processing inside the Align kernel (see pushFrame)
-    cudaStream_t fuseStream, trackStream;
-    cudaEvent_t evPre;
-    cudaEvent_t evAligned, evFused[2];
+    cudaStream_t fuseStream, trackStream, prepStream;
+    cudaEvent_t evIn, evPreR[kMapSets], evAlignedR[kMapSets];
+    cudaEvent_t evFused[kMapSets];
     bool fusePending;              // a fusion has been enqueued since the last reset
     int lastFusePar;
-    cudaGraph_t fuseGraph[2];
-    cudaGraphExec_t fuseExec[2];
-    bool haveFuseGraph[2];
+    cudaGraph_t fuseGraph[kMapSets];
+    cudaGraphExec_t fuseExec[kMapSets];
+    bool haveFuseGraph[kMapSets];
 };
 
 namespace {
@@ -72,8 +77,8 @@ int pfail(int code, const char* what, cudaError_t e = cudaSuccess) {
 
 cudaError_t enqueueIcp(vh_pipeline* p, int par, const uint16_t* d_depth, const float* d_poseIn, float* d_poseOut, cudaStream_t s, int* n) {
     vh_context* c = p->ctx;
-    const float4* tg = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelVerts : p->verts[1 - par];
-    const float4* tgN = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelNormals : p->normals[1 - par];
+    const float4* tg = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelVerts : p->verts[(par + kMapSets - 1) % kMapSets];
+    const float4* tgN = p->mode == VH_TRACK_FRAME_TO_MODEL ? p->modelNormals : p->normals[(par + kMapSets - 1) % kMapSets];
     // Partitioned context with peer mailboxes (vh_set_peers): this rank reduces its share of the image rows and the
     // 32-float all-reduce over NVLink runs inside the kernel's epilogue -- every rank must push the same frames.
     const int world = c->peers.world > 1 ? c->peers.world : 1, rank = world > 1 ? c->peers.rank : 0;
@@ -159,10 +164,12 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
     p->d_poseBuf[1] = p->d_poseBuf[0] ? p->d_poseBuf[0] + 16 : nullptr;
     p->d_pose = p->d_poseBuf[0];
     chk(cudaStreamCreateWithFlags(&p->copyStream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMapSets; ++i) {
         chk(cudaMalloc((void**)&p->verts[i], px * sizeof(float4)));
         chk(cudaMalloc((void**)&p->normals[i], px * sizeof(float4)));
         chk(cudaMalloc((void**)&p->depthf[i], px * sizeof(float)));
+    }
+    for (int i = 0; i < 2; ++i) {
         chk(cudaMalloc((void**)&p->d_depthStage[i], px * sizeof(uint16_t)));
         chk(cudaEventCreateWithFlags(&p->evCopied[i], cudaEventDisableTiming));
         chk(cudaEventCreateWithFlags(&p->evConsumed[i], cudaEventDisableTiming));
@@ -175,11 +182,14 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
         int least = 0, greatest = 0;
         chk(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         chk(cudaStreamCreateWithPriority(&p->trackStream, cudaStreamNonBlocking, greatest));
-        chk(cudaEventCreateWithFlags(&p->evPre, cudaEventDisableTiming));
+        chk(cudaStreamCreateWithPriority(&p->prepStream, cudaStreamNonBlocking, greatest));
+        chk(cudaEventCreateWithFlags(&p->evIn, cudaEventDisableTiming));
+        for (int i = 0; i < kMapSets; ++i) {
+            chk(cudaEventCreateWithFlags(&p->evPreR[i], cudaEventDisableTiming));
+            chk(cudaEventCreateWithFlags(&p->evAlignedR[i], cudaEventDisableTiming));
+        }
         chk(cudaStreamCreateWithPriority(&p->fuseStream, cudaStreamNonBlocking, least));
-        chk(cudaEventCreateWithFlags(&p->evAligned, cudaEventDisableTiming));
-        chk(cudaEventCreateWithFlags(&p->evFused[0], cudaEventDisableTiming));
-        chk(cudaEventCreateWithFlags(&p->evFused[1], cudaEventDisableTiming));
+        for (int i = 0; i < kMapSets; ++i) chk(cudaEventCreateWithFlags(&p->evFused[i], cudaEventDisableTiming));
     }
     if (mode == VH_TRACK_FRAME_TO_MODEL) {
         chk(cudaMalloc((void**)&p->modelVerts, px * sizeof(float4)));
@@ -194,20 +204,26 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
 
 void vh_pipeline_destroy(vh_pipeline* p) {
     if (!p) return;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMapSets; ++i) {
         if (p->haveGraph[i]) { cudaGraphExecDestroy(p->exec[i]); cudaGraphDestroy(p->graph[i]); }
         if (p->haveFuseGraph[i]) { cudaGraphExecDestroy(p->fuseExec[i]); cudaGraphDestroy(p->fuseGraph[i]); }
-        cudaFree(p->verts[i]); cudaFree(p->normals[i]); cudaFree(p->depthf[i]); cudaFree(p->d_depthStage[i]);
+        cudaFree(p->verts[i]); cudaFree(p->normals[i]); cudaFree(p->depthf[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(p->d_depthStage[i]);
         if (p->evCopied[i]) cudaEventDestroy(p->evCopied[i]);
         if (p->evConsumed[i]) cudaEventDestroy(p->evConsumed[i]);
     }
     if (p->copyStream) cudaStreamDestroy(p->copyStream);
     if (p->fuseStream) { cudaStreamSynchronize(p->fuseStream); cudaStreamDestroy(p->fuseStream); }
     if (p->trackStream) { cudaStreamSynchronize(p->trackStream); cudaStreamDestroy(p->trackStream); }
-    if (p->evPre) cudaEventDestroy(p->evPre);
-    if (p->evAligned) cudaEventDestroy(p->evAligned);
-    if (p->evFused[0]) cudaEventDestroy(p->evFused[0]);
-    if (p->evFused[1]) cudaEventDestroy(p->evFused[1]);
+    if (p->prepStream) { cudaStreamSynchronize(p->prepStream); cudaStreamDestroy(p->prepStream); }
+    if (p->evIn) cudaEventDestroy(p->evIn);
+    for (int i = 0; i < kMapSets; ++i) {
+        if (p->evPreR[i]) cudaEventDestroy(p->evPreR[i]);
+        if (p->evAlignedR[i]) cudaEventDestroy(p->evAlignedR[i]);
+    }
+    for (int i = 0; i < kMapSets; ++i) if (p->evFused[i]) cudaEventDestroy(p->evFused[i]);
     cudaFree(p->modelVerts); cudaFree(p->modelNormals); cudaFree(p->d_poseBuf[0]);
     delete p;
 }
@@ -217,6 +233,7 @@ int vh_pipeline_reset(vh_pipeline* p, const float* pose16_host, vh_stream s) {
     if (!p) return pfail(VH_ERR_INVALID, "vh_pipeline_reset: null pipeline");
     const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+    if (p->prepStream) PCUDA(cudaStreamSynchronize(p->prepStream));
     if (p->trackStream) PCUDA(cudaStreamSynchronize(p->trackStream));
     if (p->fuseStream) PCUDA(cudaStreamSynchronize(p->fuseStream));
     p->fusePending = false;
@@ -229,60 +246,89 @@ int vh_pipeline_reset(vh_pipeline* p, const float* pose16_host, vh_stream s) {
     return VH_OK;
 }
 
-static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, cudaEvent_t afterPreprocess) {
+// The overlapped schedule (VH_PIPE_OVERLAP).  Four streams, frame k uses map set m = k % 3:
+//   prep   [input ready] [fusion(k-3), Align(k-2) done: set m is free] -> preprocess(k)
+//   track  [preprocess(k)] -> Align(k) + pose chain                      (high priority, in order: Align(k-1) before)
+//   fuse   [Align(k)] -> frame constants(k) -> { alloc, compact, integrate }(k)
+//   caller [Align(k)]                                                     (the contract: ordered behind the pose)
+// inputOnSt: the depth image is produced by work already enqueued on the caller's stream (vh_pipeline_push_device);
+// otherwise it is complete once `ready` (may be null: now) has fired -- then preprocess(k+1) does not wait for the
+// caller's stream, i.e. not for Align(k), and the tracking chain per frame is the Align kernel alone.
+static int pushFrameOverlap(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, bool inputOnSt, cudaEvent_t ready,
+                            cudaEvent_t afterPreprocess) {
     vh_context* c = p->ctx;
-    const int par = (int)(p->frame & 1);
+    const int m = (int)(p->frame % kMapSets);
     const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
-    // overlapped schedule: the maps of this parity were read by the fusion of frame k-2 on the other stream
-    if (p->overlap && st != nullptr && p->frame >= 2) PCUDA(cudaStreamWaitEvent(st, p->evFused[par], 0));
-    // Tracked frames of the overlapped schedule CAN run the pre-processing as the prologue of the Align kernel
-    // (k_track.cu, vh_track_frame).  Measured at VGA (r2, tools/align_trace.py pre): the prologue needs 7.4 us at the
-    // persistent kernel's 16 warps per SM (5 IEEE divisions + a normalisation per pixel) + 2.7 us of fence / barrier /
-    // fence, against ~5 us for the stand-alone pass at full occupancy + one stream hand-off: 7 820 vs 8 450 frames/s.
-    // So it is opt-in (VH_PIPE_FUSED_PRE=1); the stand-alone pass stays the default.
-    const bool fusedPre = p->fusedPre && p->overlap && st != nullptr && track && c->v.bilatLut == nullptr;
-    if (!fusedPre) {
-        PCUDA(launch_preprocess(c, d_depth, p->verts[par], p->normals[par], p->depthf[par], st));   // Application.cpp:73
-        if (afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, st));  // the raw depth buffer may be overwritten from here on
-        p->launches += (c->v.bilatLut != nullptr && c->cfg.policy == VH_POLICY_FIXED) ? 2 : 1;   // [k_bilateral +] k_preprocess
+    // Tracked frames CAN run the pre-processing as the prologue of the Align kernel (k_track.cu, vh_track_frame).
+    // Measured at VGA (r2, tools/align_trace.py pre): the prologue needs 7.4 us at the persistent kernel's 16 warps per
+    // SM (5 IEEE divisions + a normalisation per pixel) + 2.7 us of fence / barrier / fence, ON the tracking chain, against
+    // a stand-alone pass that runs beside the previous Align: 7 820 vs 8 450 frames/s.  Opt-in: VH_PIPE_FUSED_PRE=1.
+    const bool fusedPre = p->fusedPre && track && c->v.bilatLut == nullptr;
+    cudaStream_t ps = fusedPre ? p->trackStream : p->prepStream;
+    if (inputOnSt) {
+        PCUDA(cudaEventRecord(p->evIn, st));
+        PCUDA(cudaStreamWaitEvent(ps, p->evIn, 0));
+    } else if (ready) {
+        PCUDA(cudaStreamWaitEvent(ps, ready, 0));
     }
+    if (p->frame >= kMapSets) PCUDA(cudaStreamWaitEvent(ps, p->evFused[m], 0));                 // fusion(k-3) read set m
+    if (p->frame >= 2) PCUDA(cudaStreamWaitEvent(ps, p->evAlignedR[(m + 1) % kMapSets], 0));     // Align(k-2) had it as target
+    if (!fusedPre) {
+        PCUDA(launch_preprocess(c, d_depth, p->verts[m], p->normals[m], p->depthf[m], ps));     // Application.cpp:73
+        if (afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, ps));  // the raw depth buffer may be overwritten from here on
+        p->launches += (c->v.bilatLut != nullptr && c->cfg.policy == VH_POLICY_FIXED) ? 2 : 1;  // [k_bilateral +] k_preprocess
+    }
+    int nIcp = 0, nFuse = 0;
+    if (track) {
+        if (!fusedPre) {
+            PCUDA(cudaEventRecord(p->evPreR[m], ps));
+            PCUDA(cudaStreamWaitEvent(p->trackStream, p->evPreR[m], 0));
+        }
+        float* next = p->d_poseBuf[p->poseIdx ^ 1];
+        // [Application.cpp:73] + CameraTracking.cpp:35-67 + the pose chain, one launch
+        PCUDA(enqueueIcp(p, m, fusedPre ? d_depth : nullptr, p->d_pose, next, p->trackStream, &nIcp));
+        p->poseIdx ^= 1;
+        p->d_pose = next;
+        PCUDA(cudaEventRecord(p->evAlignedR[m], p->trackStream));
+        if (fusedPre && afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, p->trackStream));
+    } else {
+        PCUDA(cudaEventRecord(p->evAlignedR[m], ps));
+    }
+    PCUDA(cudaStreamWaitEvent(st, p->evAlignedR[m], 0));                   // the caller's stream is ordered behind the pose
+    PCUDA(cudaStreamWaitEvent(p->fuseStream, p->evAlignedR[m], 0));
+    PCUDA(launch_set_frame_device(c, p->d_pose, nullptr, nullptr, p->fuseStream));   // SDF_Hashtable.cpp:15-21
+    if (!p->haveFuseGraph[m]) {
+        PCUDA(cudaStreamBeginCapture(p->fuseStream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = enqueueFusion(p, m, p->fuseStream, &nFuse);
+        cudaError_t e2 = cudaStreamEndCapture(p->fuseStream, &p->fuseGraph[m]);
+        if (e != cudaSuccess) return pfail(VH_ERR_CUDA, "pipeline capture", e);
+        if (e2 != cudaSuccess) return pfail(VH_ERR_CUDA, "cudaStreamEndCapture", e2);
+        PCUDA(cudaGraphInstantiate(&p->fuseExec[m], p->fuseGraph[m], 0));
+        p->haveFuseGraph[m] = true;
+    } else {
+        nFuse = 3 + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
+    }
+    PCUDA(cudaGraphLaunch(p->fuseExec[m], p->fuseStream));
+    PCUDA(cudaEventRecord(p->evFused[m], p->fuseStream));
+    p->fusePending = true;
+    p->lastFusePar = m;
+    p->launches += nIcp + 1 + nFuse;
+    p->frame += 1;
+    return VH_OK;
+}
+
+static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, bool inputOnSt, cudaEvent_t ready, cudaEvent_t afterPreprocess) {
+    if (p->overlap && st != nullptr) return pushFrameOverlap(p, d_depth, st, inputOnSt, ready, afterPreprocess);
+    vh_context* c = p->ctx;
+    const int par = (int)(p->frame % kMapSets);            // map set of this frame
+    const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
+    if (!inputOnSt && ready) PCUDA(cudaStreamWaitEvent(st, ready, 0));
+    PCUDA(launch_preprocess(c, d_depth, p->verts[par], p->normals[par], p->depthf[par], st));   // Application.cpp:73
+    if (afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, st));      // the raw depth buffer may be overwritten from here on
+    p->launches += (c->v.bilatLut != nullptr && c->cfg.policy == VH_POLICY_FIXED) ? 2 : 1;   // [k_bilateral +] k_preprocess
     int n = 0;
-    if (p->overlap && st != nullptr) {
-        int nIcp = 0, nFuse = 0;
-        if (track) {
-            PCUDA(cudaEventRecord(p->evPre, st));                          // the frame (and, unfused, its maps) are ready
-            PCUDA(cudaStreamWaitEvent(p->trackStream, p->evPre, 0));
-            float* next = p->d_poseBuf[p->poseIdx ^ 1];
-            // Application.cpp:73-75 + CameraTracking.cpp:35-67 + the pose chain, one launch
-            PCUDA(enqueueIcp(p, par, fusedPre ? d_depth : nullptr, p->d_pose, next, p->trackStream, &nIcp));
-            p->poseIdx ^= 1;
-            p->d_pose = next;
-            PCUDA(cudaEventRecord(p->evAligned, p->trackStream));
-            PCUDA(cudaStreamWaitEvent(st, p->evAligned, 0));               // the caller's stream is ordered behind the pose
-            if (fusedPre && afterPreprocess) PCUDA(cudaEventRecord(afterPreprocess, st));
-        } else {
-            PCUDA(cudaEventRecord(p->evAligned, st));
-        }
-        PCUDA(cudaStreamWaitEvent(p->fuseStream, p->evAligned, 0));
-        PCUDA(launch_set_frame_device(c, p->d_pose, nullptr, nullptr, p->fuseStream));   // SDF_Hashtable.cpp:15-21
-        if (!p->haveFuseGraph[par]) {
-            PCUDA(cudaStreamBeginCapture(p->fuseStream, cudaStreamCaptureModeThreadLocal));
-            cudaError_t e = enqueueFusion(p, par, p->fuseStream, &nFuse);
-            cudaError_t e2 = cudaStreamEndCapture(p->fuseStream, &p->fuseGraph[par]);
-            if (e != cudaSuccess) return pfail(VH_ERR_CUDA, "pipeline capture", e);
-            if (e2 != cudaSuccess) return pfail(VH_ERR_CUDA, "cudaStreamEndCapture", e2);
-            PCUDA(cudaGraphInstantiate(&p->fuseExec[par], p->fuseGraph[par], 0));
-            p->haveFuseGraph[par] = true;
-        } else {
-            nFuse = 3 + (c->cfg.policy == VH_POLICY_REF_EXACT ? 1 : 0);
-        }
-        PCUDA(cudaGraphLaunch(p->fuseExec[par], p->fuseStream));
-        PCUDA(cudaEventRecord(p->evFused[par], p->fuseStream));
-        p->fusePending = true;
-        p->lastFusePar = par;
-        n = nIcp + 1 + nFuse;
-    } else if (track && p->useGraph && st != nullptr) {
-        // frame-to-model always reads maps[par] too, so keep one graph per parity in both modes
+    if (track && p->useGraph && st != nullptr) {
+        // one graph per map set (the graph bakes in the set's addresses and those of its predecessor, the ICP target)
         if (!p->haveGraph[par]) {
             PCUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             cudaError_t e = enqueueBody(p, par, true, st, &n);
@@ -307,7 +353,16 @@ static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, c
 
 int vh_pipeline_push_device(vh_pipeline* p, const uint16_t* d_depth, vh_stream s) {
     if (!p || !d_depth) return pfail(VH_ERR_INVALID, "vh_pipeline_push_device: null argument");
-    return pushFrame(p, d_depth, reinterpret_cast<cudaStream_t>(s), nullptr);
+    return pushFrame(p, d_depth, reinterpret_cast<cudaStream_t>(s), true, nullptr, nullptr);
+}
+
+// Same, for a depth image that is NOT produced on stream s: it is complete in device memory once `ready` (a cudaEvent_t,
+// may be NULL = already complete) has fired.  With VH_PIPE_OVERLAP the pre-processing then runs beside the tracking of the
+// previous frame instead of behind it.  The buffer must stay untouched until the frame has been pre-processed (i.e.
+// until s, which is ordered behind the frame's pose, gets there).
+int vh_pipeline_push_device_ready(vh_pipeline* p, const uint16_t* d_depth, void* ready_event, vh_stream s) {
+    if (!p || !d_depth) return pfail(VH_ERR_INVALID, "vh_pipeline_push_device_ready: null argument");
+    return pushFrame(p, d_depth, reinterpret_cast<cudaStream_t>(s), false, reinterpret_cast<cudaEvent_t>(ready_event), nullptr);
 }
 
 // e2e entry: depth in (pinned) host memory, pose back to host memory; returns after enqueueing.
@@ -321,9 +376,8 @@ int vh_pipeline_push_host(vh_pipeline* p, const uint16_t* h_depth, float* h_pose
     if (p->hostFrames >= 2) PCUDA(cudaStreamWaitEvent(p->copyStream, p->evConsumed[slot], 0));
     PCUDA(cudaMemcpyAsync(p->d_depthStage[slot], h_depth, bytes, cudaMemcpyHostToDevice, p->copyStream));
     PCUDA(cudaEventRecord(p->evCopied[slot], p->copyStream));
-    PCUDA(cudaStreamWaitEvent(st, p->evCopied[slot], 0));
     p->hostFrames += 1;
-    int rc = pushFrame(p, p->d_depthStage[slot], st, p->evConsumed[slot]);
+    int rc = pushFrame(p, p->d_depthStage[slot], st, false, p->evCopied[slot], p->evConsumed[slot]);
     if (rc != VH_OK) return rc;
     if (h_pose_out16) PCUDA(cudaMemcpyAsync(h_pose_out16, p->d_pose, 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return VH_OK;
@@ -357,14 +411,14 @@ int vh_pipeline_pose_async(vh_pipeline* p, float* h_pose16, vh_stream s) {
 // Dense metric depth (W x H floats) of the latest pushed frame, as the Fixed integration reads it.
 int vh_pipeline_depthf(vh_pipeline* p, float** d_depthf) {
     if (!p || !d_depthf || p->frame == 0) return pfail(VH_ERR_INVALID, "vh_pipeline_depthf: bad argument / no frame yet");
-    *d_depthf = p->depthf[(int)((p->frame - 1) & 1)];
+    *d_depthf = p->depthf[(int)((p->frame - 1) % kMapSets)];
     return VH_OK;
 }
 
 // which: 0 = maps of the latest pushed frame, 1 = ICP target of the NEXT frame's tracking
 int vh_pipeline_maps(vh_pipeline* p, int which, float4** verts, float4** normals) {
     if (!p || !verts || !normals || p->frame == 0) return pfail(VH_ERR_INVALID, "vh_pipeline_maps: bad argument / no frame yet");
-    const int last = (int)((p->frame - 1) & 1);
+    const int last = (int)((p->frame - 1) % kMapSets);
     if (which == 1 && p->mode == VH_TRACK_FRAME_TO_MODEL) { *verts = p->modelVerts; *normals = p->modelNormals; }
     else { *verts = p->verts[last]; *normals = p->normals[last]; }
     return VH_OK;

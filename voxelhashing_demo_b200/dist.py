@@ -53,6 +53,11 @@ class PartitionedTracker:
         # two landing buffers: the copy + broadcast of frame k+1 run on their own stream while frame k is being tracked
         self._depths = [torch.zeros(n, dtype=dt, device="cuda"), torch.zeros(n, dtype=dt, device="cuda")]
         self.depth = self._depths[0]
+        # Everything the tracker enqueues goes to its OWN stream: the overlapped schedule of the native pipeline (CUDA graph
+        # capture, the Align / fusion side streams) is not available on the legacy default stream, which is what a caller
+        # who never set a stream hands in.  push(input_ready=False) / reset order it behind the caller's current stream,
+        # flush() orders the caller's current stream behind it.
+        self.stream = torch.cuda.Stream()
         self._bcast_stream = torch.cuda.Stream()
         self._ev_arrived = [torch.cuda.Event(), torch.cuda.Event()]
         self._ev_consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -117,6 +122,12 @@ class PartitionedTracker:
 
     def flush(self):
         """Order the current stream behind the fusion of the latest pushed frame (no-op without overlap)."""
+        cur = self.torch.cuda.current_stream()
+        with self.torch.cuda.stream(self.stream):
+            self._flush_own()
+        cur.wait_stream(self.stream)
+
+    def _flush_own(self):
         if self.pipe is not None:
             self.pipe.flush()
             return
@@ -125,14 +136,16 @@ class PartitionedTracker:
             self._fuse_pending = False
 
     def reset(self, pose):
-        self.flush()
-        if self.pipe is not None:
-            self.pipe.reset(np.ascontiguousarray(pose, dtype=np.float32))
+        self.stream.wait_stream(self.torch.cuda.current_stream())
+        with self.torch.cuda.stream(self.stream):
+            self._flush_own()
+            if self.pipe is not None:
+                self.pipe.reset(np.ascontiguousarray(pose, dtype=np.float32))
+                self.frame = 0
+                return
+            self.d_pose.copy_(self.torch.from_numpy(np.ascontiguousarray(pose, dtype=np.float32).reshape(16)))
+            self.ctx.icp_reset(True)
             self.frame = 0
-            return
-        self.d_pose.copy_(self.torch.from_numpy(np.ascontiguousarray(pose, dtype=np.float32).reshape(16)))
-        self.ctx.icp_reset(True)
-        self.frame = 0
 
     def push(self, d_depth=None, input_ready: bool = False):
         """One frame.  Rank 0 passes the depth image (device tensor, or pinned host tensor for the end-to-end
@@ -140,8 +153,14 @@ class PartitionedTracker:
         resident sequence, a pinned host buffer filled earlier): the copy + broadcast then start right away on their
         own stream and overlap the tracking of the previous frame.  Otherwise they are ordered behind everything
         enqueued on the current stream so far, which is always safe."""
+        if not input_ready:
+            self.stream.wait_stream(self.torch.cuda.current_stream())
+        with self.torch.cuda.stream(self.stream):
+            self._push(d_depth, input_ready)
+
+    def _push(self, d_depth, input_ready):
         ctx, dist, torch = self.ctx, self.dist, self.torch
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream()                   # = self.stream
         slot = self._pushed & 1
         self.depth = self._depths[slot]
         bs = self._bcast_stream
@@ -157,15 +176,17 @@ class PartitionedTracker:
             if self.world > 1:
                 dist.broadcast(self.depth.view(torch.uint8), src=0, group=self.group)   # raw bytes over NVLink / NVSwitch
             self._ev_arrived[slot].record(bs)
-        main.wait_event(self._ev_arrived[slot])
         self._pushed += 1
         if self.pipe is not None:
             l0 = self.pipe.launches()
-            self.pipe.push_device(self.depth)
+            # the landing buffer is complete when the broadcast has arrived -- an event, not this stream: the pre-processing of
+            # frame k+1 then runs beside the Align of frame k instead of behind it
+            self.pipe.push_device_ready(self.depth, self._ev_arrived[slot])
             self._ev_consumed[slot].record(main)             # conservative: recorded behind the whole push, not only the pre-processing
             self.launches += self.pipe.launches() - l0
             self.frame += 1
             return
+        main.wait_event(self._ev_arrived[slot])
         par = self.frame & 1
         v, n, df = self.maps[par]
         pv, pn, _ = self.maps[1 - par]
@@ -184,7 +205,7 @@ class PartitionedTracker:
                     ctx.icp_solve(self.sys)
                     self.launches += 2
         # the frame constants and per-frame counters change now: the previous frame's fusion must be through
-        self.flush()
+        self._flush_own()
         if self.frame > 0:
             ctx.pose_compose(self.d_pose, self.d_pose)        # T_k = T_{k-1} * delta, also publishes the frame pose
         else:
@@ -208,19 +229,22 @@ class PartitionedTracker:
         self.frame += 1
 
     def pose(self) -> np.ndarray:
-        if self.pipe is not None:
-            p = self.pipe.pose()
+        with self.torch.cuda.stream(self.stream):
+            if self.pipe is not None:
+                p = self.pipe.pose()
+                self.torch.cuda.synchronize()
+                return p
             self.torch.cuda.synchronize()
-            return p
-        self.torch.cuda.synchronize()
-        return self.d_pose.cpu().numpy().reshape(4, 4)
+            return self.d_pose.cpu().numpy().reshape(4, 4)
 
     def pose_async(self, h_pose_pinned):
-        """Stream-ordered D2H of the current pose into a pinned host tensor of 16 floats (the e2e read-back)."""
-        if self.pipe is not None:
-            self.pipe.pose_async(h_pose_pinned)
-        else:
-            h_pose_pinned.copy_(self.d_pose, non_blocking=True)
+        """Stream-ordered D2H of the current pose into a pinned host tensor of 16 floats (the e2e read-back); valid after
+        flush() + a synchronisation of the caller's stream."""
+        with self.torch.cuda.stream(self.stream):
+            if self.pipe is not None:
+                self.pipe.pose_async(h_pose_pinned)
+            else:
+                h_pose_pinned.copy_(self.d_pose, non_blocking=True)
 
     def last_depthf(self):
         """Dense metric depth of the latest frame: device address (native pipeline) or tensor (Python loop)."""

@@ -191,6 +191,9 @@ class Context:
     def alloc_blocks(self, verts, normals=None, stream=None):
         L.check(self.lib.vh_alloc_blocks(self._h, _ptr(verts), _ptr(normals), _stream(stream)), "vh_alloc_blocks")
 
+    def set_tuning(self, align_ctas: int = 0, fusion_reserved_sms: int = -1):
+        L.check(self.lib.vh_set_tuning(self._h, align_ctas, fusion_reserved_sms), "vh_set_tuning")
+
     def alloc_blocks_depth(self, depth_u16, stream=None):
         """Allocation straight from the raw u16 depth image (2 B / pixel; same blocks as from the vertex map)."""
         L.check(self.lib.vh_alloc_blocks_depth(self._h, _ptr(depth_u16), _stream(stream)), "vh_alloc_blocks_depth")
@@ -434,6 +437,13 @@ class FramePipeline:
 
     def push_device(self, d_depth, stream=None):
         L.check(self.lib.vh_pipeline_push_device(self._p, _ptr(d_depth), _stream(stream)), "vh_pipeline_push_device")
+
+    def push_device_ready(self, d_depth, ready_event=None, stream=None):
+        """One frame whose depth image is not produced on `stream`: complete once `ready_event` (a torch.cuda.Event that has
+        been recorded, or None = complete already) has fired.  Overlapped schedule: its pre-processing runs beside the
+        tracking of the previous frame."""
+        ev = 0 if ready_event is None else int(ready_event.cuda_event)
+        L.check(self.lib.vh_pipeline_push_device_ready(self._p, _ptr(d_depth), ev, _stream(stream)), "vh_pipeline_push_device_ready")
 
     def push_host(self, h_depth, h_pose_out=None, stream=None):
         L.check(self.lib.vh_pipeline_push_host(self._p, _ptr(h_depth), _ptr(h_pose_out), _stream(stream)), "vh_pipeline_push_host")

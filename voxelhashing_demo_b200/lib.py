@@ -101,14 +101,14 @@ LEGACY_SYMBOLS = [
 ]
 HANDLE_SYMBOLS = [
     "vh_last_error", "vh_default_config", "vh_device_count", "vh_create", "vh_destroy", "vh_reset", "vh_get_config",
-    "vh_set_intrinsics", "vh_set_intrinsic_matrices", "vh_bytes_allocated", "vh_preprocess", "vh_set_pose",
+    "vh_set_intrinsics", "vh_set_intrinsic_matrices", "vh_set_tuning", "vh_bytes_allocated", "vh_preprocess", "vh_set_pose",
     "vh_set_pose_device", "vh_alloc_blocks", "vh_alloc_blocks_depth", "vh_compact", "vh_integrate", "vh_integrate_depthf", "vh_fuse_frame",
     "vh_get_stats", "vh_garbage_collect", "vh_stream_out", "vh_stream_in", "vh_icp_reset", "vh_icp_iterate", "vh_icp_align", "vh_track_frame", "vh_icp_reduce", "vh_icp_solve", "vh_icp_get",
     "vh_icp_set_delta", "vh_set_peers", "vh_peer_bytes", "vh_icp_align_rows", "vh_icp_delta_device", "vh_pose_compose", "vh_icp_reduce_corr", "vh_find_correspondences",
     "vh_jacobians", "vh_raycast", "vh_export_entries", "vh_export_compact", "vh_export_block",
     "vh_compact_table_device", "vh_compact_counter_device", "vh_voxel_blocks_device", "vh_save", "vh_load",
     "vh_dump_text", "vh_extract_mesh", "vh_save_mesh_ply", "vh_depth_read", "vh_depth_free", "vh_depth_write_png", "vh_depth_last_error",
-    "vh_pipeline_create", "vh_pipeline_flush", "vh_pipeline_destroy", "vh_pipeline_reset", "vh_pipeline_push_device",
+    "vh_pipeline_create", "vh_pipeline_flush", "vh_pipeline_destroy", "vh_pipeline_reset", "vh_pipeline_push_device", "vh_pipeline_push_device_ready",
     "vh_pipeline_push_host", "vh_pipeline_pose", "vh_pipeline_pose_device", "vh_pipeline_pose_async", "vh_pipeline_depthf", "vh_pipeline_maps", "vh_pipeline_launches",
 ]
 
@@ -139,6 +139,7 @@ def load_library() -> C.CDLL:
     lib.vh_set_intrinsics.argtypes = [P, F, F, F, F]
     lib.vh_set_intrinsic_matrices.argtypes = [P, P, P]
     lib.vh_bytes_allocated.argtypes = [P]
+    lib.vh_set_tuning.argtypes = [P, I, I]
     lib.vh_bytes_allocated.restype = C.c_ulonglong
     lib.vh_preprocess.argtypes = [P, P, P, P, P, P]
     lib.vh_set_pose.argtypes = [P, P, P]
@@ -194,6 +195,7 @@ def load_library() -> C.CDLL:
     lib.vh_pipeline_destroy.restype = None
     lib.vh_pipeline_reset.argtypes = [P, P, P]
     lib.vh_pipeline_push_device.argtypes = [P, P, P]
+    lib.vh_pipeline_push_device_ready.argtypes = [P, P, P, P]
     lib.vh_pipeline_push_host.argtypes = [P, P, P, P]
     lib.vh_pipeline_pose.argtypes = [P, P, P]
     lib.vh_pipeline_pose_async.argtypes = [P, P, P]
