@@ -552,7 +552,7 @@ def run_partitioned(args, rank, world, local):
     if rank == 0 and multi and not args.no_single:
         cfg1, _, _, _ = workload_config(name, 1, 0)
         ctx1 = Context(cfg1)
-        t1 = PartitionedTracker(ctx1, 0, 1, overlap=bool(args.overlap))
+        t1 = PartitionedTracker(ctx1, 0, 1, overlap=bool(args.overlap))       # default scheduling: what a 1-GPU user gets
         # (timed_run uses dist.barrier when multi: the single-GPU leg runs on rank 0 alone, so it is written out here)
         t1.reset(poses[order[0]].astype(np.float32))
         for i in range(W):
@@ -579,7 +579,8 @@ def run_partitioned(args, rank, world, local):
         dist.barrier()
 
     ctx = Context(cfg)
-    tracker = PartitionedTracker(ctx, rank, world, overlap=bool(args.overlap))
+    tuning = (args.align_ctas, args.reserve_sms) if args.align_ctas > 0 else None
+    tracker = PartitionedTracker(ctx, rank, world, overlap=bool(args.overlap), tuning=tuning)
     l0 = tracker.launches
     with ClockSampler(local) as cs:
         ms_local, host_enqueue_ms = timed_run(tracker, d_frames if rank == 0 else None)
@@ -699,6 +700,7 @@ def run_partitioned(args, rank, world, local):
                          "voxel_updates_per_s_all_ranks": upd_stage / (t_int * 1e-6),
                          "note": "achieved = mean per-GPU algorithmic bytes (16 N_upd + 16 N_vis + 4 W H) / the slowest rank's launch time"},
             "gpu_launches": int(launches),
+            "scheduling": {"align_ctas": tracker.tuning[0], "sms_reserved_for_align": tracker.tuning[1]} if tracker.tuning else "default (Align on all SMs but 8)",
             "host_enqueue_ms_per_step": host_enqueue_ms / K, "clocks": cs.summary(),
             "single_gpu_same_workload": single,
             "speedup_vs_single_gpu_same_workload": (K / (ms / 1e3)) / single["value"] if single else None,
@@ -812,6 +814,8 @@ def main():
     ap.add_argument("--overlap", type=int, default=1, help="1: fuse frame k beside the tracking of frame k+1 (VH_PIPE_OVERLAP); 0: strictly serial frames")
     ap.add_argument("--ready", type=int, default=0, help="N=1 device-resident leg: 1 = vh_pipeline_push_device_ready (input complete, no producer on the stream), 0 = vh_pipeline_push_device")
     ap.add_argument("--repeats", type=int, default=5, help="N=1: how many times the W warm-up + K timed steps pass is repeated (median reported)")
+    ap.add_argument("--align-ctas", type=int, default=0, help="partitioned runs: CTAs of the persistent Align kernel (0 = automatic)")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="partitioned runs: SMs the integrate grid leaves free for the Align grid")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hbm", action="store_true", help="skip the large-volume integrate roofline leg")
     ap.add_argument("--no-refexact", action="store_true", help="skip the RefExact leg of the repo's own kernels")

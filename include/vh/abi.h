@@ -144,6 +144,7 @@ typedef struct vh_stats {
     unsigned long long numUpdated;   /* voxels updated by the last integrate call */
     int lastInserted;       /* blocks inserted by the last allocation call */
     int lastFreed;          /* blocks released by the last vh_garbage_collect call */
+    int overflowLeaked;     /* overflow-arena slots lost to append races since creation (counted in overflowUsed, never linked) */
 } vh_stats;
 
 /* ICP normal equations, (v, omega) unknown order (ref Solver.cu:25-37, SE3.cpp:4-19):

@@ -304,9 +304,9 @@ int insertFixed(vo_table* t, I3 key) {
     if (claim >= 0) {
         Entry& e = t->table[claim];
         int id = popHeap(t);
-        if (id < 0) {                                   // heap empty: never-used bucket slot stays free, anything else a tombstone
+        if (id < 0) {                                   // heap empty: the claimed slot ALWAYS becomes a tombstone {key, FREE}, as on the device
             t->heapCounter++; t->dropped++;
-            if (e.pos.x != kIntMax || (unsigned)claim >= S) e.pos = key;
+            e.pos = key;
             return -1;
         }
         e.pos = key; e.ptr = id * 512;

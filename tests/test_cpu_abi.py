@@ -94,12 +94,28 @@ def test_product_never_touches_the_oracle():
 
 
 def test_sass_has_the_blackwell_paths(built_library):
-    """The allocation claim is a single 128-bit CAS; integration moves voxels with 128-bit accesses."""
+    """The sm_100a instructions the design depends on are in the shipped SASS (excerpt: profiles/r2_sass_excerpt.txt):
+    allocation claims a slot with ONE 128-bit CAS; integration moves a thread's four voxels with ONE 256-bit access
+    (sm_100+) and evaluates them with packed fp32x2 arithmetic (FFMA2, sm_100+); allocation de-duplicates with MATCH.ANY;
+    the persistent Align kernel exchanges {value, sequence} words with 64-bit strong (relaxed-scope) loads / stores --
+    .GPU inside the grid, .SYS across NVLink -- and contains no ticket atomics."""
+    import re
+
     sass = subprocess.run(["cuobjdump", "-sass", str(L.LIB_PATH)], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    assert "ATOMG.E.CAS.128" in sass
-    assert "LDG.E.128" in sass and "STG.E.128" in sass
-    assert "MATCH.ANY" in sass and "REDUX" in sass or "MATCH.ANY" in sass
+
+    def count(pat):
+        return len(re.findall(pat, sass))
+
+    assert count(r"ATOMG\.E\.CAS\.128") >= 2
+    assert count(r"LDG\.E\.[A-Z0-9.]*256") >= 8 and count(r"STG\.E\.[A-Z0-9.]*256") >= 8
+    assert count(r"\bFFMA2\b") >= 60
+    assert count(r"MATCH\.ANY") >= 4 and count(r"\bREDUX\b") >= 1
+    assert count(r"LDG\.E\.64\.STRONG\.GPU") >= 8 and count(r"STG\.E\.64\.STRONG\.GPU") >= 4
+    assert count(r"LDG\.E\.64\.STRONG\.SYS") >= 8 and count(r"STG\.E\.64\.STRONG\.SYS") >= 8
+    # the Align kernels: no global atomics at all (the exchange is store + poll)
+    align = re.findall(r"Function : \S*k_icp_align\S*\n(.*?)(?=\n\s*Function : |\Z)", sass, flags=re.S)
+    assert len(align) == 4 and all("ATOMG" not in a and "RED.E" not in a for a in align)
 
 
 def test_invalid_configs_are_rejected_before_touching_a_device(built_library):

@@ -19,7 +19,10 @@ METRICS = [
     "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "smsp__inst_executed.sum",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
     "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum", "l1tex__t_set_conflicts_pipe_lsu_mem_global_op_atom.sum",
+    "l1tex__t_set_conflicts_pipe_lsu_mem_global_op_red.sum",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
 ]
 
 
@@ -51,7 +54,7 @@ def main():
                 v = v / 1000 if unit.startswith("n") else (v * 1000 if unit.startswith("m") else v)
                 per.setdefault(name, []).append(v)
         tot = sum(sum(v) for v in per.values())
-        out = [f"# {tag} launch list: ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120, `python tools/prof_target.py frame 2`",
+        out = [f"# {tag} launch list: ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120, `python tools/prof_target.py frame 3` (tools/gpu_profile.sh)",
                "# config C2, steady-state frames of the graph-replayed pipeline; per-launch times are cold-cache and serialised: compare SHARES",
                f"{'kernel':45s} {'launches':>8s} {'mean_us':>9s} {'share_%':>8s}"]
         for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):

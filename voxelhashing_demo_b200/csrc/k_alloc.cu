@@ -30,12 +30,15 @@ __device__ __forceinline__ bool packKey(int x, int y, int z, unsigned long long&
     return true;
 }
 
-__device__ __forceinline__ bool finishInsert(const View& v, unsigned slot, int x, int y, int z, bool keepKey) {
+__device__ __forceinline__ bool finishInsert(const View& v, unsigned slot, int x, int y, int z) {
     int addr = atomicSub(&v.ctr->heapCounter, 1);           // ref allocSingleBlockInHeap :331
     if (addr < 0) {                                         // heap exhausted: the reference reads out of bounds here (Q6)
         atomicAdd(&v.ctr->heapCounter, 1);
-        // a never-used in-bucket slot goes back to free; a linked arena entry or a reclaimed slot stays a tombstone {key, FREE}
-        v.entries[slot] = keepKey ? make_int4(x, y, z, VH_FREE_BLOCK) : freeSlot();
+        // ALWAYS a tombstone {key, FREE}, never back to "never used": while this slot was LOCKED a peer with another key may
+        // have claimed the NEXT slot (and the last heap block) -- a never-used slot in front of a live one would end every
+        // scan early and hide that block from lookups (raycast, mesh) and from later inserts of its own key.  Tombstones
+        // are claimable and keep the scan going.
+        v.entries[slot] = make_int4(x, y, z, VH_FREE_BLOCK);
         atomicAdd(&v.ctr->dropped, 1);
         return false;
     }
@@ -90,7 +93,7 @@ __device__ int insertFixed(const View& v, int x, int y, int z, bool& fresh) {
         if (claim >= 0) {
             int4 old;
             if (casSlot(v.entries + claim, claimSeen, want, old)) {
-                fresh = finishInsert(v, (unsigned)claim, x, y, z, claimSeen.x != VH_FREE_COORD || (unsigned)claim >= v.numSlots);
+                fresh = finishInsert(v, (unsigned)claim, x, y, z);
                 return fresh ? claim : -1;
             }
             if (old.w != VH_FREE_BLOCK && sameKey(old, x, y, z)) return claim;   // a peer won the slot with the same key
@@ -105,7 +108,7 @@ __device__ int insertFixed(const View& v, int x, int y, int z, bool& fresh) {
         __threadfence();                                    // entry visible before it can be reached through the link
         while (true) {
             const int prev = atomicCAS(v.chain + cur, 0, mySlot - (int)cur);
-            if (prev == 0) { fresh = finishInsert(v, (unsigned)mySlot, x, y, z, true); return fresh ? mySlot : -1; }
+            if (prev == 0) { fresh = finishInsert(v, (unsigned)mySlot, x, y, z); return fresh ? mySlot : -1; }
             // a peer appended first: step onto its entry and try again behind it
             cur += (unsigned)prev;
             ++len;
@@ -113,7 +116,8 @@ __device__ int insertFixed(const View& v, int x, int y, int z, bool& fresh) {
             if ((e.w != VH_FREE_BLOCK && sameKey(e, x, y, z)) || len >= v.chainMax) {
                 const bool present = e.w != VH_FREE_BLOCK && sameKey(e, x, y, z);
                 if (!present) atomicAdd(&v.ctr->dropped, 1);
-                v.entries[mySlot] = make_int4(x, y, z, VH_FREE_BLOCK);     // never linked: invisible, leaked
+                v.entries[mySlot] = make_int4(x, y, z, VH_FREE_BLOCK);     // never linked: invisible, leaked -- and counted
+                atomicAdd(&v.ctr->arenaLeaked, 1);
                 return present ? (int)cur : -1;
             }
         }

@@ -329,6 +329,7 @@ int vh_get_stats(vh_context* c, vh_stats* out, vh_stream s) {
     out->numUpdated = h.numUpdated;
     out->lastInserted = h.lastInserted;
     out->lastFreed = h.gcFreed;
+    out->overflowLeaked = h.arenaLeaked;
     return VH_OK;
 }
 
@@ -532,7 +533,7 @@ int vh_save(vh_context* c, const char* path) {
     VH_CUDA(cudaDeviceSynchronize());
     FILE* f = fopen(path, "wb");
     if (!f) return fail(VH_ERR_INVALID, "vh_save: cannot open file");
-    CkptHeader h{{'V', 'H', 'B', '2', '0', '0', 0, 0}, 2, c->v.numBuckets, c->v.bucketSize, c->v.numVoxelBlocks, c->v.overflowSlots,
+    CkptHeader h{{'V', 'H', 'B', '2', '0', '0', 0, 0}, 3, c->v.numBuckets, c->v.bucketSize, c->v.numVoxelBlocks, c->v.overflowSlots,
                  (unsigned)c->cfg.policy, c->v.voxelSize};
     Counters ctr;
     cudaMemcpy(&ctr, c->v.ctr, sizeof(ctr), cudaMemcpyDeviceToHost);
@@ -562,7 +563,7 @@ int vh_load(vh_context* c, const char* path) {
     CkptHeader h;
     Counters ctr;
     bool ok = fread(&h, sizeof(h), 1, f) == 1 && fread(&ctr, sizeof(ctr), 1, f) == 1;
-    if (!ok || memcmp(h.magic, "VHB200", 6) != 0 || h.version != 2 || h.numBuckets != c->v.numBuckets || h.bucketSize != c->v.bucketSize ||
+    if (!ok || memcmp(h.magic, "VHB200", 6) != 0 || h.version != 3 || h.numBuckets != c->v.numBuckets || h.bucketSize != c->v.bucketSize ||
         h.numVoxelBlocks != c->v.numVoxelBlocks || h.overflowSlots != c->v.overflowSlots) {
         fclose(f);
         return fail(VH_ERR_INVALID, "vh_load: checkpoint does not match this context's geometry");

@@ -39,6 +39,7 @@ struct Counters {
     int gcFreed;                  // blocks released by the last garbage-collection pass
     int streamCount;              // blocks moved by the last stream-out / stream-in pass
     int meshCount;                // triangles produced by the last mesh extraction
+    int arenaLeaked;              // overflow-arena slots taken by an append that lost its race and were never linked (lost until vh_reset)
 };
 
 struct FrameParams {

@@ -38,9 +38,11 @@ def owner_of(x: int, y: int, z: int, parts: int) -> int:
 class PartitionedTracker:
     """Per-rank driver of one partition: broadcast -> preprocess -> split ICP + all-reduce -> fuse."""
 
-    def __init__(self, ctx, rank: int, world: int, iterations: int | None = None, group=None, overlap: bool = True):
+    def __init__(self, ctx, rank: int, world: int, iterations: int | None = None, group=None, overlap: bool = True,
+                 tuning: tuple[int, int] | None = None):
         """overlap: fuse frame k on a second stream beside the broadcast / pre-processing / tracking of frame k+1
-        (frame-to-frame ICP does not read the model); results are identical, the model lags the pose until flush()."""
+        (frame-to-frame ICP does not read the model); results are identical, the model lags the pose until flush().
+        tuning = (Align CTAs, SMs the persistent integrate grid leaves free), None = automatic: see _auto_tuning."""
         import torch
         import torch.distributed as dist
 
@@ -74,6 +76,11 @@ class PartitionedTracker:
         self._ev_pose = torch.cuda.Event() if self.overlap else None
         self._ev_fused = torch.cuda.Event() if self.overlap else None
         self._fuse_pending = False
+        if tuning is None:
+            tuning = self._auto_tuning(cfg, world)
+        if tuning is not None and overlap:
+            ctx.set_tuning(int(tuning[0]), int(tuning[1]))
+        self.tuning = tuning
         if world > 1:
             self._setup_peer_exchange()
         # With the exchange fused into the ICP kernel the whole frame is stream-ordered device work, so it goes through
@@ -86,6 +93,20 @@ class PartitionedTracker:
 
             self.pipe = FramePipeline(ctx, iterations=self.iterations, mode=FramePipeline.FRAME_TO_FRAME, use_graph=True,
                                       overlap=self.overlap)
+
+    @staticmethod
+    def _auto_tuning(cfg, world: int):
+        """The Align grid (one 512-thread CTA per SM, the whole register file of each) and the persistent integrate grid
+        cannot share an SM.  With a few image rows per rank the Align is a chain of exchange latencies, not work: a SMALL
+        grid (~6 pixels per thread) on its own SMs costs it little and lets tracking(k+1) run beside fusion(k) instead of
+        after it.  Measured on C4 at 2 mm (r2): 8 GPUs, 36 Align CTAs + 36 reserved SMs: 3 015 frames/s against 2 319 with the
+        default grid (Align 161 -> 199 us, integrate 205 -> 235 us, but side by side).  At 2-4 GPUs the fusion is several
+        times longer than the Align and giving up a quarter of the SMs costs more than the overlap returns."""
+        if world < 8:
+            return None
+        rows = (cfg.height + world - 1) // world
+        ctas = max(16, min(64, (rows * cfg.width + 3071) // 3072))
+        return ctas, ctas
 
     def _setup_peer_exchange(self):
         """Symmetric (peer-mapped) exchange regions so the 32-float all-reduce runs INSIDE the ICP kernel's

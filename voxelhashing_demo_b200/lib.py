@@ -80,6 +80,7 @@ class VhStats(C.Structure):
         ("numUpdated", C.c_ulonglong),
         ("lastInserted", C.c_int),
         ("lastFreed", C.c_int),
+        ("overflowLeaked", C.c_int),
     ]
 
 
