@@ -366,6 +366,32 @@ int  vh_pipeline_depthf(vh_pipeline* p, float** d_depthf);   /* dense metric dep
 int  vh_pipeline_maps(vh_pipeline* p, int which, float4** d_verts, float4** d_normals);
 long long vh_pipeline_launches(vh_pipeline* p);   /* kernels launched so far */
 
+/* ---- multi-GPU from C / C++ (one process per GPU of one node; CUDA IPC peer memory over NVLink / NVSwitch) -----------
+ * The block-coordinate hash space is partitioned with vh_config::partCount / partRank; what the ranks exchange is (1)
+ * every depth frame and (2) the 32-float ICP system of every Gauss-Newton iteration.  Both go
+ * through one exchange region per rank that every other rank maps:
+ *     vh_dist_create      allocates this rank's region (ICP mailboxes + three frame landing buffers + flags)
+ *     vh_dist_export      its 64-byte CUDA IPC handle -- the host program hands the handles of all ranks around
+ *                         (MPI_Allgather, a socket, files: examples/dist_app.cpp uses files)
+ *     vh_dist_connect     maps the other ranks' regions (handles: world x vh_dist_handle_bytes(), in rank order) and
+ *                         registers the mailboxes with the context (vh_set_peers): from here on vh_icp_align_rows /
+ *                         vh_track_frame / the pipeline carry the all-reduce INSIDE the persistent Align kernel
+ *     vh_dist_broadcast_frame   rank 0 passes the frame (device memory, complete once stream s gets there), the others
+ *                         NULL; rank 0's kernel stores it straight into every rank's landing buffer (no NCCL, no host
+ *                         hop).  Every rank receives the address of its copy and the cudaEvent_t that fires when it is
+ *                         complete -- the arguments of vh_pipeline_push_device_ready
+ *     vh_dist_frame_consumed    stream s has pre-processed the oldest outstanding frame (e.g. the stream a frame was
+ *                         pushed on, which is ordered behind its pose): rank 0 may overwrite that landing buffer
+ * Every rank must broadcast / push the same number of frames (the fused all-reduce waits for every rank). */
+typedef struct vh_dist vh_dist;
+int  vh_dist_create(vh_context* ctx, int rank, int world, vh_dist** out);
+unsigned long long vh_dist_handle_bytes(void);
+int  vh_dist_export(vh_dist* d, void* handle_out);
+int  vh_dist_connect(vh_dist* d, const void* handles_by_rank);
+int  vh_dist_broadcast_frame(vh_dist* d, const uint16_t* d_depth_rank0, const uint16_t** d_frame, void** ready_event, vh_stream s);
+int  vh_dist_frame_consumed(vh_dist* d, vh_stream s);
+void vh_dist_destroy(vh_dist* d);
+
 #ifdef __cplusplus
 }
 #endif

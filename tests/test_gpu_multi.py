@@ -101,3 +101,40 @@ def test_partitioned_fused_equals_single(built_library, tmp_path, world):
     off = int((diff > 1e-4).sum())
     assert off <= max(3, int(2e-5 * diff.size)), f"{off} of {diff.size} voxels differ by more than 1e-4 (worst {diff.max():.4f})"
     assert float(np.median(diff)) < 1e-6
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cxx_host_path_vh_dist(built_library, tmp_path, world):
+    """The multi-GPU frame loop driven from C++ ONLY (examples/dist_app.cpp: fork per GPU, CUDA IPC handles through files,
+    vh_dist_broadcast_frame + vh_pipeline_push_device_ready, the all-reduce inside the Align kernel): every rank ends with
+    the bit-identical pose, equal to the one-process run within 1e-6, and the ranks' blocks add up to the single table."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import subprocess
+
+    from voxelhashing_demo_b200 import scenes
+
+    exe = Path(built_library).parent / "vh_dist_app"
+    assert exe.exists()
+    W, H, n = 640, 480, 6
+    poses = [scenes.trajectory_C2(3 * k) for k in range(n)]
+    frames = np.stack([scenes.render_depth(scenes.scene_S1T(), p, W, H, 517.3, 516.5, 318.6, 255.3) for p in poses]).astype(np.uint16)
+    frames.tofile(tmp_path / "frames.bin")
+    out = {}
+    for w in (1, world):
+        prefix = tmp_path / f"w{w}"
+        r = subprocess.run([str(exe), str(tmp_path / "frames.bin"), str(W), str(H), str(n), str(w), str(prefix), "8"],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-3000:]
+        out[w] = ([np.fromfile(f"{prefix}.pose.{k}", dtype=np.float32).reshape(4, 4) for k in range(w)],
+                  [tuple(int(x) for x in open(f"{prefix}.stats.{k}").read().split()) for k in range(w)])
+    single_pose, single_stats = out[1][0][0], out[1][1][0]
+    ranks, stats = out[world]
+    for p in ranks[1:]:
+        assert np.array_equal(p.view(np.uint32), ranks[0].view(np.uint32))       # no second broadcast: identical sums, identical solve
+    assert np.max(np.abs(ranks[0] - single_pose)) < 1e-6
+    # the first frame is fused at the identity pose (no reset pose given): track the relative motion
+    truth = np.linalg.inv(poses[0]) @ poses[-1]
+    assert np.max(np.abs(single_pose[:3, 3] - truth[:3, 3])) < 5e-3
+    assert abs(sum(s[0] for s in stats) - single_stats[0]) <= 2 and all(s[2] == 0 for s in stats)
+    assert all(s[0] > 0.5 * single_stats[0] / world for s in stats)               # every rank owns a share

@@ -20,6 +20,7 @@ CSRC = PKG / "csrc"
 OBJ = PKG / "_obj"
 LIB = PKG / "libvh_b200.so"
 HOST_DEMO = PKG / "vh_headless_app"
+DIST_DEMO = PKG / "vh_dist_app"
 
 NVCC = os.environ.get("VH_NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -113,6 +114,12 @@ def _build_locked(verbose: bool, force: bool) -> Path:
         _link_if_stale(HOST_DEMO, OBJ / "vh_headless_app.stamp", demo_want,
                        [NVCC, "-std=c++17", "-O2", "-ccbin", HOSTCXX, "-I", str(ROOT / "include"), str(demo_src), "-o", str(HOST_DEMO),
                         "-L", str(PKG), "-lvh_b200", "-Xlinker", f"-rpath={PKG}", "-Xlinker", "-rpath=$ORIGIN"], "headless_app build", force)
+    dist_src = ROOT / "examples" / "dist_app.cpp"
+    if dist_src.exists():                          # the multi-GPU frame loop from C++ (vh_dist_*): one process per GPU
+        dist_want = hashlib.sha256((lib_want + hashlib.sha256(dist_src.read_bytes()).hexdigest()).encode()).hexdigest()
+        _link_if_stale(DIST_DEMO, OBJ / "vh_dist_app.stamp", dist_want,
+                       [NVCC, "-std=c++17", "-O2", "-ccbin", HOSTCXX, "-I", str(ROOT / "include"), str(dist_src), "-o", str(DIST_DEMO),
+                        "-L", str(PKG), "-lvh_b200", "-Xlinker", f"-rpath={PKG}", "-Xlinker", "-rpath=$ORIGIN"], "dist_app build", force)
     return LIB
 
 

@@ -318,7 +318,8 @@ static int pushFrameOverlap(vh_pipeline* p, const uint16_t* d_depth, cudaStream_
 }
 
 static int pushFrame(vh_pipeline* p, const uint16_t* d_depth, cudaStream_t st, bool inputOnSt, cudaEvent_t ready, cudaEvent_t afterPreprocess) {
-    if (p->overlap && st != nullptr) return pushFrameOverlap(p, d_depth, st, inputOnSt, ready, afterPreprocess);
+    // (the legacy default stream is fine here: nothing is captured on the caller's stream, it only records / waits for events)
+    if (p->overlap) return pushFrameOverlap(p, d_depth, st, inputOnSt, ready, afterPreprocess);
     vh_context* c = p->ctx;
     const int par = (int)(p->frame % kMapSets);            // map set of this frame
     const bool track = p->frame > 0 && p->mode != VH_TRACK_NONE;
