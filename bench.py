@@ -631,9 +631,9 @@ def run_partitioned(args, rank, world, local):
     torch.cuda.synchronize()
     stages = {}
     maps_a, maps_b = ctx.new_maps(), ctx.new_maps()
-    d_last = tracker.depth                                           # the broadcast landing buffer of the latest frame
+    d_prev, d_last = tracker.last_frames()                           # this rank's landing buffers: the frame before (ICP target) and the latest
     ctx.preprocess(d_last, *maps_a)
-    ctx.preprocess(tracker._depths[(tracker._pushed) & 1], *maps_b)   # the frame before it: the ICP target
+    ctx.preprocess(d_prev, *maps_b)
     rows = tracker.rows
 
     def timed(fn, r=4):
@@ -681,7 +681,8 @@ def run_partitioned(args, rank, world, local):
             "data": "synthetic",
             "config": dict(config_dict(name, cfg, n_unique),
                            partition=f"hash space partitioned over {world} GPU(s) (owner = mix(block) mod {world}), {cfg.numVoxelBlocks} blocks per GPU; "
-                                     "frame broadcast over NVLink (NCCL); 32-float ICP all-reduce "
+                                     + ("frame stored by rank 0 straight into every rank's landing buffer over NVLink (vh_dist, CUDA IPC, no NCCL on the data path)"
+                                        if getattr(tracker, "_dist", None) is not None else "frame broadcast over NVLink (NCCL)") + "; 32-float ICP all-reduce "
                                      + ("FUSED into the persistent Align kernel over NVLink peer memory" if tracker.fused else
                                         ("through NCCL" if multi else "n/a (one GPU)")),
                            l2="per-frame voxel working set exceeds L2 on every rank"),

@@ -46,9 +46,11 @@ __global__ void __launch_bounds__(256) k_frame_push(Regions reg, int world, cons
         while (ldAcquireSys(consumed) + kSlots < seq) { }
     }
     __syncthreads();
-    for (int p = 0; p < world; ++p) {
-        uint4* dst = reinterpret_cast<uint4*>(reg.r[p] + kLandingOffset + (size_t)slot * landingStride);
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = __ldg(src + i);
+    // read once (the source may be pinned HOST memory: the frame then crosses the host link exactly once), store P times
+    const size_t off = kLandingOffset + (size_t)slot * landingStride;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 w = __ldg(src + i);
+        for (int p = 0; p < world; ++p) reinterpret_cast<uint4*>(reg.r[p] + off)[i] = w;
     }
     __threadfence_system();                                  // this thread's stores are performed system-wide
     __syncthreads();
@@ -155,7 +157,7 @@ int vh_dist_connect(vh_dist* d, const void* handles) {
     return VH_OK;
 }
 
-// Rank 0 passes the frame (device memory, complete once stream s gets here); every other rank passes NULL.  Every rank
+// Rank 0 passes the frame (device memory or pinned host memory, complete once stream s gets here); every other rank passes NULL.  Every rank
 // gets the address of its landing buffer and the event that fires when the frame is complete in it.
 int vh_dist_broadcast_frame(vh_dist* d, const uint16_t* d_depth, const uint16_t** d_frame, void** ready_event, vh_stream s) {
     if (!d || !d_frame || !ready_event || (d->rank == 0 && !d_depth)) return dfail(VH_ERR_INVALID, "vh_dist_broadcast_frame: bad argument");

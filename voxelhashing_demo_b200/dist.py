@@ -81,8 +81,12 @@ class PartitionedTracker:
         if tuning is not None and overlap:
             ctx.set_tuning(int(tuning[0]), int(tuning[1]))
         self.tuning = tuning
+        self._frame_ptrs = (0, 0)                            # device addresses of the (previous, latest) frame as this rank holds them
+        self._dist = None                                   # vh_dist handle (C ABI transport: CUDA IPC, no NCCL on the data path)
         if world > 1:
-            self._setup_peer_exchange()
+            self._setup_ipc_transport()
+            if self._dist is None:
+                self._setup_peer_exchange()
         # With the exchange fused into the ICP kernel the whole frame is stream-ordered device work, so it goes through
         # the native frame pipeline (CUDA graphs; the host enqueues ~5 calls per frame instead of ~30 -- the Python
         # loop below needed 0.4 ms of host time per frame and capped the 4- and 8-GPU runs).  The NCCL-per-iteration
@@ -107,6 +111,64 @@ class PartitionedTracker:
         rows = (cfg.height + world - 1) // world
         ctas = max(16, min(64, (rows * cfg.width + 3071) // 3072))
         return ctas, ctas
+
+    def _setup_ipc_transport(self):
+        """The library's own transport (vh_dist_*, csrc/vh_dist.cu): one CUDA IPC region per rank holding the ICP mailboxes
+        and the frame landing buffers; torch.distributed only carries the 64-byte handles once.  Rank 0's kernel stores
+        every frame straight into the peers' landing buffers -- no NCCL broadcast, no stream hand-off."""
+        import ctypes as C
+        import sys
+
+        torch, dist = self.torch, self.dist
+        lib = self.ctx.lib
+        ok, why = 0, ""
+        handle = C.c_void_p()
+        try:
+            if lib.vh_dist_create(self.ctx._h, self.rank, self.world, C.byref(handle)) != 0:
+                raise RuntimeError("vh_dist_create failed")
+            hb = int(lib.vh_dist_handle_bytes())
+            mine = (C.c_ubyte * hb)()
+            if lib.vh_dist_export(handle, mine) != 0:
+                raise RuntimeError("vh_dist_export failed")
+            ok = 1
+        except Exception as e:  # noqa: BLE001
+            why = str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)           # collective decision, as below
+        if int(flag.item()) == 1:
+            t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device="cuda")
+            allh = [torch.zeros_like(t) for _ in range(self.world)]
+            dist.all_gather(allh, t, group=self.group)
+            blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            rc = lib.vh_dist_connect(handle, buf)
+            flag = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self._dist = handle
+            self.fused = True
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+        else:
+            if handle:
+                lib.vh_dist_destroy(handle)
+            print(f"[rank {self.rank}] vh_dist transport unavailable" + (f" ({why})" if why else "") + "; trying symmetric memory + NCCL broadcast",
+                  file=sys.stderr)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
+    def close(self):
+        if getattr(self, "_dist", None) is not None:
+            if self.pipe is not None:
+                self.pipe.close()
+                self.pipe = None
+            self.torch.cuda.synchronize()
+            self.ctx.lib.vh_dist_destroy(self._dist)
+            self._dist = None
 
     def _setup_peer_exchange(self):
         """Symmetric (peer-mapped) exchange regions so the 32-float all-reduce runs INSIDE the ICP kernel's
@@ -182,6 +244,29 @@ class PartitionedTracker:
     def _push(self, d_depth, input_ready):
         ctx, dist, torch = self.ctx, self.dist, self.torch
         main = torch.cuda.current_stream()                   # = self.stream
+        if self._dist is not None:
+            # the library's transport: rank 0's kernel stores the frame (device or pinned host source) into every rank's
+            # landing buffer; the pipeline pre-processes it as soon as its arrival event fires
+            import ctypes as C
+
+            frame, ready = C.c_void_p(), C.c_void_p()
+            src = None
+            if self.rank == 0:
+                src = d_depth.data_ptr()
+                if d_depth.is_cuda:
+                    d_depth.record_stream(main)
+            L_check = self.ctx.lib.vh_dist_broadcast_frame(self._dist, src, C.byref(frame), C.byref(ready), main.cuda_stream)
+            if L_check != 0:
+                raise RuntimeError("vh_dist_broadcast_frame failed")
+            self._frame_ptrs = (self._frame_ptrs[1], int(frame.value))
+            self._pushed += 1
+            l0 = self.pipe.launches()
+            self.pipe.push_device_ready(int(frame.value), int(ready.value))
+            if self.ctx.lib.vh_dist_frame_consumed(self._dist, main.cuda_stream) != 0:
+                raise RuntimeError("vh_dist_frame_consumed failed")
+            self.launches += self.pipe.launches() - l0
+            self.frame += 1
+            return
         slot = self._pushed & 1
         self.depth = self._depths[slot]
         bs = self._bcast_stream
@@ -198,6 +283,7 @@ class PartitionedTracker:
                 dist.broadcast(self.depth.view(torch.uint8), src=0, group=self.group)   # raw bytes over NVLink / NVSwitch
             self._ev_arrived[slot].record(bs)
         self._pushed += 1
+        self._frame_ptrs = (self._frame_ptrs[1], int(self.depth.data_ptr()))
         if self.pipe is not None:
             l0 = self.pipe.launches()
             # the landing buffer is complete when the broadcast has arrived -- an event, not this stream: the pre-processing of
@@ -266,6 +352,10 @@ class PartitionedTracker:
                 self.pipe.pose_async(h_pose_pinned)
             else:
                 h_pose_pinned.copy_(self.d_pose, non_blocking=True)
+
+    def last_frames(self) -> tuple[int, int]:
+        """Device addresses of the (previous, latest) raw depth frames in this rank's landing buffers."""
+        return self._frame_ptrs
 
     def last_depthf(self):
         """Dense metric depth of the latest frame: device address (native pipeline) or tensor (Python loop)."""

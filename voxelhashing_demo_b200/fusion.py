@@ -442,7 +442,7 @@ class FramePipeline:
         """One frame whose depth image is not produced on `stream`: complete once `ready_event` (a torch.cuda.Event that has
         been recorded, or None = complete already) has fired.  Overlapped schedule: its pre-processing runs beside the
         tracking of the previous frame."""
-        ev = 0 if ready_event is None else int(ready_event.cuda_event)
+        ev = 0 if ready_event is None else (int(ready_event) if isinstance(ready_event, int) else int(ready_event.cuda_event))
         L.check(self.lib.vh_pipeline_push_device_ready(self._p, _ptr(d_depth), ev, _stream(stream)), "vh_pipeline_push_device_ready")
 
     def push_host(self, h_depth, h_pose_out=None, stream=None):

@@ -198,6 +198,14 @@ def load_library() -> C.CDLL:
     lib.vh_pipeline_reset.argtypes = [P, P, P]
     lib.vh_pipeline_push_device.argtypes = [P, P, P]
     lib.vh_pipeline_push_device_ready.argtypes = [P, P, P, P]
+    lib.vh_dist_create.argtypes = [P, I, I, P]
+    lib.vh_dist_handle_bytes.restype = C.c_ulonglong
+    lib.vh_dist_export.argtypes = [P, P]
+    lib.vh_dist_connect.argtypes = [P, P]
+    lib.vh_dist_broadcast_frame.argtypes = [P, P, P, P, P]
+    lib.vh_dist_frame_consumed.argtypes = [P, P]
+    lib.vh_dist_destroy.argtypes = [P]
+    lib.vh_dist_destroy.restype = None
     lib.vh_pipeline_push_host.argtypes = [P, P, P, P]
     lib.vh_pipeline_pose.argtypes = [P, P, P]
     lib.vh_pipeline_pose_async.argtypes = [P, P, P]
