@@ -813,7 +813,7 @@ def main():
                     help="C2 (default at N=1), C3 (720p, 5 mm), C4 (2 mm large volume; default at N>1 and under torchrun), "
                          "C5 (C2 tracked frame-to-model: raycast in the loop)")
     ap.add_argument("--overlap", type=int, default=1, help="1: fuse frame k beside the tracking of frame k+1 (VH_PIPE_OVERLAP); 0: strictly serial frames")
-    ap.add_argument("--ready", type=int, default=0, help="N=1 device-resident leg: 1 = vh_pipeline_push_device_ready (input complete, no producer on the stream), 0 = vh_pipeline_push_device")
+    ap.add_argument("--ready", type=int, default=1, help="N=1 device-resident leg: 1 = vh_pipeline_push_device_ready (input complete, no producer on the stream), 0 = vh_pipeline_push_device")
     ap.add_argument("--repeats", type=int, default=5, help="N=1: how many times the W warm-up + K timed steps pass is repeated (median reported)")
     ap.add_argument("--align-ctas", type=int, default=0, help="partitioned runs: CTAs of the persistent Align kernel (0 = automatic)")
     ap.add_argument("--reserve-sms", type=int, default=0, help="partitioned runs: SMs the integrate grid leaves free for the Align grid")

@@ -752,11 +752,16 @@ def test_checkpoint_roundtrip_and_dump(built_library, oracle, tmp_path):
 
 
 # ---- full-size, size-independent properties (configs C2 / C3) --------------------------------------
-@pytest.mark.parametrize("name", ["C2", "C3"])
+@pytest.mark.parametrize("name", ["C2", "C3", "C4"])
 def test_full_size_properties(built_library, oracle, name):
     if name == "C2":
         cfg = fixed_cfg(numVoxelBlocks=65536)
         scene, traj = scenes.scene_S1T(), scenes.trajectory_C2
+    elif name == "C4":   # BASELINE.json configs[3] as stated: building-scale scene at 2 mm voxels (1.2 M blocks = 4.9 GB in one frame)
+        cfg = fixed_cfg(width=1280, height=720, fx=1034.6, fy=1033.0, cx=637.2, cy=382.95, voxelSize=0.002, truncation=0.008,
+                        truncScale=0.001, numBuckets=4000037, numVoxelBlocks=1310720, overflowSlots=524288, depthMax=12.5,
+                        maxIntegrationDistance=12.5)
+        scene, traj = scenes.scene_S3(), lambda k: scenes.trans(0, 0, 0.5) @ scenes.trajectory_C3(k)
     else:
         cfg = fixed_cfg(width=1280, height=720, fx=1034.6, fy=1033.0, cx=637.2, cy=382.95, voxelSize=0.005, truncation=0.02,
                         numBuckets=1000003, numVoxelBlocks=262144, overflowSlots=65536, depthMax=8.0, maxIntegrationDistance=8.0)
@@ -794,6 +799,17 @@ def test_full_size_properties(built_library, oracle, name):
     rep, nvis, nupd = ot.fuse_frame(pose, ov, odf)
     assert (rep.inserted, nvis, nupd) == (s1.numAllocated, s1.numVisible, int(s1.numUpdated))
     assert entries_to_set(ent) == entries_to_set(ot.entries())
+    # ... and of the voxels themselves on a sample of blocks, bit for bit (the oracle has fused the frame once, the GPU twice:
+    # compare against a fresh context that fused it once)
+    once = Context(cfg)
+    v1, n1, df1 = gpu_preprocess(once, depth)
+    once.fuse_frame(pose, v1, n1, df1)
+    ent1 = once.export_entries()
+    for e in ent1[:: max(1, len(ent1) // 64)]:
+        g = once.export_block(int(e["ptr"]))
+        o = ot.block(int(e["x"]), int(e["y"]), int(e["z"]))
+        assert o is not None
+        assert np.array_equal(bits(g["sdf"]), bits(o[:, 0])) and np.array_equal(bits(g["weight"]), bits(o[:, 1]))
 
 
 # ---- edge cases: empty, ragged, degenerate inputs -----------------------------------------------------

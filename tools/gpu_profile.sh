@@ -14,6 +14,8 @@ cap() {  # name, kernel regex, skip, target args...
 }
 cap align k_icp_align 3 icp 1
 cap alloc k_alloc 4 frame 1
+cap allocinsert k_alloc 0 alloc
+cap allocsteady k_alloc 1 alloc
 cap compact k_compact 4 frame 1
 cap preprocess k_preprocess 4 frame 1
 cap integrate k_integrate 1 integrate 3

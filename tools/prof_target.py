@@ -32,6 +32,19 @@ if what == "integrate":          # large-volume integrate: working set > 2x L2
     torch.cuda.synchronize()
     st = ctx.stats()
     print("visible", st.numVisible, "updated", st.numUpdated, "alloc", st.numAllocated, "dropped", st.dropped)
+elif what == "alloc":            # insert-heavy allocation: the FIRST frame of the 4 mm large-volume scene (355 k new blocks), then a steady-state pass
+    cfg, scene, traj, _ = bench.workload_config("C4_4mm")
+    ctx = Context(cfg)
+    pose = traj(0).astype(np.float32)
+    d = torch.from_numpy(scenes.render_depth(scene, pose, cfg.width, cfg.height, cfg.fx, cfg.fy, cfg.cx, cfg.cy).reshape(-1)).cuda()
+    v, n, df = ctx.new_maps()
+    ctx.preprocess(d, v, n, df)
+    ctx.set_pose(pose)
+    ctx.alloc_blocks_depth(d)        # launch 0: every block is new
+    ctx.alloc_blocks_depth(d)        # launch 1: every block is present
+    torch.cuda.synchronize()
+    st = ctx.stats()
+    print("alloc", st.numAllocated, "dropped", st.dropped, "overflow", st.overflowUsed)
 elif what in ("icp", "frame", "raycast"):
     cfg, scene, traj, _ = bench.workload_config("C2")
     ctx = Context(cfg)

@@ -15,9 +15,13 @@
 // full spill into the overflow arena through a lock-free chain append (CAS on the tail's link).
 // RefExact keeps the reference's rule bit for bit: a per-bucket atomicExch try-lock that is never
 // released inside a frame, so at most one new block per bucket per frame (quirk Q4).
+#include <cooperative_groups.h>
+
 #include "vh_device.cuh"
 
 namespace vh {
+
+namespace cg = cooperative_groups;
 
 constexpr int kFilterSize = 128;
 constexpr unsigned long long kFilterEmpty = ~0ull;
@@ -30,8 +34,14 @@ __device__ __forceinline__ bool packKey(int x, int y, int z, unsigned long long&
     return true;
 }
 
+// Warp-aggregated: the lanes of a warp that reach this point together pop the free list with ONE atomicSub.  (r2 ncu, 355 k
+// inserts in one launch: 2.24 L2 atomic sectors per new block -- slot CAS, heap pop, insert count -- with or without the
+// aggregation: after the match / filter / probe stages the surviving lanes of a warp rarely get here in the same cycle.)
 __device__ __forceinline__ bool finishInsert(const View& v, unsigned slot, int x, int y, int z) {
-    int addr = atomicSub(&v.ctr->heapCounter, 1);           // ref allocSingleBlockInHeap :331
+    const cg::coalesced_group g = cg::coalesced_threads();
+    int base = 0;
+    if (g.thread_rank() == 0) base = atomicSub(&v.ctr->heapCounter, (int)g.size());   // ref allocSingleBlockInHeap :331, size() pops at once
+    const int addr = g.shfl(base, 0) - (int)g.thread_rank();
     if (addr < 0) {                                         // heap exhausted: the reference reads out of bounds here (Q6)
         atomicAdd(&v.ctr->heapCounter, 1);
         // ALWAYS a tombstone {key, FREE}, never back to "never used": while this slot was LOCKED a peer with another key may
@@ -45,7 +55,8 @@ __device__ __forceinline__ bool finishInsert(const View& v, unsigned slot, int x
     unsigned id = v.heap[addr];                             // ref :333
     v.blockInfo[id] = make_int4(x, y, z, (int)slot);
     reinterpret_cast<volatile int*>(v.entries + slot)[3] = (int)(id * 512u);   // ref :449-451 (ptr = id*512)
-    atomicAdd(&v.ctr->lastInserted, 1);
+    const cg::coalesced_group ok = cg::coalesced_threads();
+    if (ok.thread_rank() == 0) atomicAdd(&v.ctr->lastInserted, (int)ok.size());
     return true;
 }
 

@@ -176,9 +176,10 @@ int vh_create(const vh_config* cfg, vh_context** out) {
     chk(devAlloc(c, &c->icpPartials, (size_t)kIcpMaxBlocks * 32));
     chk(devAlloc(c, &c->icpLL, kIcpLLWords));
     if (e == cudaSuccess) chk(cudaMemset(c->icpLL, 0, sizeof(unsigned long long) * kIcpLLWords));   // sequence 0 = never written
-    // persistent Align grid: a few SMs stay free so that the fusion of the previous frame (other stream) can run
-    // beside the tracking of this one (r2: 140 of 148 CTAs -> +7 % frames/s at VGA, Align itself +0.7 %)
-    c->icpCtas = c->numSMs > 32 ? c->numSMs - 8 : c->numSMs;
+    // persistent Align grid: a few SMs stay free so that the pre-processing of the next frame and the fusion of the previous
+    // one (other streams) can run beside the tracking of this one.  r2 sweep at VGA, frames/s device-resident / end to end:
+    // 148: 7 770 / -, 144: 8 840 / 8 250, 140: 8 800 / 8 620, 136: 9 230 / 9 240, 132: 8 600 / 9 210, 120: 8 430 / 8 990
+    c->icpCtas = c->numSMs > 32 ? c->numSMs - 12 : c->numSMs;
     if (const char* env = getenv("VH_ICP_CTAS")) c->icpCtas = atoi(env);
     if (const char* env = getenv("VH_FUSION_RESERVE_SMS")) c->fusionReserveSMs = atoi(env);
 #ifdef VH_TIMELINE
