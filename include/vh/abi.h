@@ -145,6 +145,7 @@ typedef struct vh_stats {
     int lastInserted;       /* blocks inserted by the last allocation call */
     int lastFreed;          /* blocks released by the last vh_garbage_collect call */
     int overflowLeaked;     /* overflow-arena slots lost to append races since creation (counted in overflowUsed, never linked) */
+    int exchangeTimeouts;   /* multi-GPU: Aligns stopped because a peer's ICP contribution did not arrive within ~5 s (a rank died) */
 } vh_stats;
 
 /* ICP normal equations, (v, omega) unknown order (ref Solver.cu:25-37, SE3.cpp:4-19):
@@ -390,6 +391,7 @@ int  vh_dist_export(vh_dist* d, void* handle_out);
 int  vh_dist_connect(vh_dist* d, const void* handles_by_rank);
 int  vh_dist_broadcast_frame(vh_dist* d, const uint16_t* d_depth_rank0, const uint16_t** d_frame, void** ready_event, vh_stream s);
 int  vh_dist_frame_consumed(vh_dist* d, vh_stream s);
+int  vh_dist_timeouts(vh_dist* d);     /* waits given up after ~5 s (a rank died): > 0 means the frames since then are not to be trusted; synchronises */
 void vh_dist_destroy(vh_dist* d);
 
 #ifdef __cplusplus

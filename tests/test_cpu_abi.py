@@ -113,9 +113,9 @@ def test_sass_has_the_blackwell_paths(built_library):
     assert count(r"MATCH\.ANY") >= 4 and count(r"\bREDUX\b") >= 1
     assert count(r"LDG\.E\.64\.STRONG\.GPU") >= 8 and count(r"STG\.E\.64\.STRONG\.GPU") >= 4
     assert count(r"LDG\.E\.64\.STRONG\.SYS") >= 8 and count(r"STG\.E\.64\.STRONG\.SYS") >= 8
-    # the Align kernels: no global atomics at all (the exchange is store + poll)
+    # the Align kernels: the exchange is store + poll -- the only global atomic is the time-out counter of the cross-GPU wait
     align = re.findall(r"Function : \S*k_icp_align\S*\n(.*?)(?=\n\s*Function : |\Z)", sass, flags=re.S)
-    assert len(align) == 4 and all("ATOMG" not in a and "RED.E" not in a for a in align)
+    assert len(align) == 4 and all(a.count("ATOMG") + a.count("RED.E") <= 1 for a in align)
 
 
 def test_invalid_configs_are_rejected_before_touching_a_device(built_library):

@@ -399,12 +399,17 @@ __device__ __forceinline__ void peerScatter(const PeerView& pv, float mine, unsi
     const int lane = threadIdx.x & 31;
     for (int p = 0; p < pv.world; ++p) llStoreSys(peerWord(pv, p, seq & 1u, pv.rank, lane), mine, seq);
 }
+// Bounded: a peer that died or never launched must not hang this GPU inside a kernel.  After kPeerSpinCycles the lane gives
+// up, counts the time-out and returns NaN -- the solve then refuses (non-finite), every CTA stops the Align in the same
+// iteration, and the host finds vh_stats::exchangeTimeouts > 0.
 __device__ __forceinline__ float peerGather(const PeerView& pv, unsigned seq) {
     const int lane = threadIdx.x & 31;
     unsigned long long w[kMaxPeers];
 #pragma unroll
     for (int r = 0; r < kMaxPeers; ++r) w[r] = r < pv.world ? llLoadSys(peerWord(pv, pv.rank, seq & 1u, r, lane)) : 0ull;
     float t = 0.f;
+    long long t0 = 0;
+    bool timing = false;
 #pragma unroll
     for (int r = 0; r < kMaxPeers; ++r) {
         if (r >= pv.world) break;
@@ -412,6 +417,11 @@ __device__ __forceinline__ float peerGather(const PeerView& pv, unsigned seq) {
 #if VH_PEER_BACKOFF > 0
             __nanosleep(VH_PEER_BACKOFF);                    // the mailbox lines are the target of the peers' NVLink stores
 #endif
+            if (!timing) { t0 = clock64(); timing = true; }
+            else if (clock64() - t0 > kPeerSpinCycles) {
+                if (lane == 0 && pv.timeouts) atomicAdd(pv.timeouts, 1);
+                return __int_as_float(0x7fc00000);
+            }
             w[r] = llLoadSys(peerWord(pv, pv.rank, seq & 1u, r, lane));
         }
         t += llValue(w[r]);

@@ -331,6 +331,7 @@ int vh_get_stats(vh_context* c, vh_stats* out, vh_stream s) {
     out->lastInserted = h.lastInserted;
     out->lastFreed = h.gcFreed;
     out->overflowLeaked = h.arenaLeaked;
+    out->exchangeTimeouts = h.exchangeTimeouts;
     return VH_OK;
 }
 
@@ -414,6 +415,7 @@ int vh_set_peers(vh_context* c, int rank, int world, void* const* bufs) {
     c->peers.world = world;
     c->peers.rank = rank;
     for (int p = 0; p < kMaxPeers; ++p) c->peers.buf[p] = (p < world && bufs) ? static_cast<float*>(bufs[p]) : nullptr;
+    c->peers.timeouts = &c->v.ctr->exchangeTimeouts;
     return VH_OK;
 }
 unsigned long long vh_peer_bytes(void) { return (unsigned long long)kPeerBytes; }

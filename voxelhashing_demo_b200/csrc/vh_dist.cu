@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kSlots = 3;
 constexpr size_t kFlagOffset = (kPeerBytes + 255) & ~(size_t)255;
-constexpr size_t kFlagBytes = 256;                          // arrived[3] at +0, consumed[8] at +64
+constexpr size_t kFlagBytes = 256;                          // arrived[3] at +0, consumed[8] at +64, time-out count at +128
 constexpr size_t kLandingOffset = kFlagOffset + kFlagBytes;
 
 __device__ __forceinline__ unsigned long long ldAcquireSys(const unsigned long long* p) {
@@ -43,7 +43,12 @@ __global__ void __launch_bounds__(256) k_frame_push(Regions reg, int world, cons
     // the slot still holds frame seq - 1 - kSlots until every rank has consumed it
     if (threadIdx.x < (unsigned)world && seq > (unsigned long long)kSlots) {
         const unsigned long long* consumed = reinterpret_cast<const unsigned long long*>(reg.r[0] + kFlagOffset + 64) + threadIdx.x;
-        while (ldAcquireSys(consumed) + kSlots < seq) { }
+        const long long t0 = clock64();
+        while (ldAcquireSys(consumed) + kSlots < seq)
+            if (clock64() - t0 > kPeerSpinCycles) {          // a rank died: overwrite the slot rather than hang; counted, see vh_dist_timeouts
+                atomicAdd(reinterpret_cast<unsigned long long*>(reg.r[0] + kFlagOffset + 128), 1ull);
+                break;
+            }
     }
     __syncthreads();
     // read once (the source may be pinned HOST memory: the frame then crosses the host link exactly once), store P times
@@ -68,7 +73,12 @@ __global__ void __launch_bounds__(256) k_frame_push(Regions reg, int world, cons
 __global__ void k_frame_wait(const unsigned char* region, int slot, unsigned long long seq) {
     if (threadIdx.x == 0) {
         const unsigned long long* arrived = reinterpret_cast<const unsigned long long*>(region + kFlagOffset) + slot;
-        while (ldAcquireSys(arrived) < seq) { }
+        const long long t0 = clock64();
+        while (ldAcquireSys(arrived) < seq)
+            if (clock64() - t0 > kPeerSpinCycles) {          // rank 0 died or never pushed: give up instead of hanging the GPU
+                atomicAdd(const_cast<unsigned long long*>(reinterpret_cast<const unsigned long long*>(region + kFlagOffset + 128)), 1ull);
+                break;
+            }
     }
 }
 
@@ -189,6 +199,15 @@ int vh_dist_frame_consumed(vh_dist* d, vh_stream s) {
     k_frame_consumed<<<1, 32, 0, reinterpret_cast<cudaStream_t>(s)>>>(d->peers.r[0], d->rank, d->consumed);
     DCUDA(cudaGetLastError());
     return VH_OK;
+}
+
+// Frames this rank stopped waiting for (a peer died or never pushed); synchronises.
+int vh_dist_timeouts(vh_dist* d) {
+    if (!d) return -1;
+    unsigned long long n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(&n, d->region + kFlagOffset + 128, sizeof(n), cudaMemcpyDeviceToHost);
+    return (int)n;
 }
 
 void vh_dist_destroy(vh_dist* d) {

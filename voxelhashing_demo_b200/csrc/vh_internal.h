@@ -40,6 +40,7 @@ struct Counters {
     int streamCount;              // blocks moved by the last stream-out / stream-in pass
     int meshCount;                // triangles produced by the last mesh extraction
     int arenaLeaked;              // overflow-arena slots taken by an append that lost its race and were never linked (lost until vh_reset)
+    int exchangeTimeouts;         // cross-GPU exchanges given up after kPeerSpinCycles (a peer died or never launched): the Align stops
 };
 
 struct FrameParams {
@@ -97,7 +98,9 @@ constexpr int kBilatLut = 1024;      // |delta depth| >= this many raw units con
 constexpr int kMaxPeers = 8;
 // exchange region: 2 parity slots x kMaxPeers ranks x 32 values x {float value, u32 sequence}
 constexpr size_t kPeerBytes = 2 * kMaxPeers * 32 * 8;
-struct PeerView { int world, rank; float* buf[kMaxPeers]; };
+struct PeerView { int world, rank; float* buf[kMaxPeers]; int* timeouts; };
+// a rank that waits longer than this for a peer's contribution gives up (about 5 s at 2 GHz) instead of hanging the GPU
+constexpr long long kPeerSpinCycles = 10000000000ll;
 
 struct Pose16f { float m[16]; };
 

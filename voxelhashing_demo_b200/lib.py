@@ -81,6 +81,7 @@ class VhStats(C.Structure):
         ("lastInserted", C.c_int),
         ("lastFreed", C.c_int),
         ("overflowLeaked", C.c_int),
+        ("exchangeTimeouts", C.c_int),
     ]
 
 
@@ -111,7 +112,7 @@ HANDLE_SYMBOLS = [
     "vh_dump_text", "vh_extract_mesh", "vh_save_mesh_ply", "vh_depth_read", "vh_depth_free", "vh_depth_write_png", "vh_depth_last_error",
     "vh_pipeline_create", "vh_pipeline_flush", "vh_pipeline_destroy", "vh_pipeline_reset", "vh_pipeline_push_device", "vh_pipeline_push_device_ready",
     "vh_pipeline_push_host", "vh_pipeline_pose", "vh_pipeline_pose_device", "vh_pipeline_pose_async", "vh_pipeline_depthf", "vh_pipeline_maps", "vh_pipeline_launches",
-    "vh_dist_create", "vh_dist_handle_bytes", "vh_dist_export", "vh_dist_connect", "vh_dist_broadcast_frame", "vh_dist_frame_consumed", "vh_dist_destroy",
+    "vh_dist_create", "vh_dist_handle_bytes", "vh_dist_export", "vh_dist_connect", "vh_dist_broadcast_frame", "vh_dist_frame_consumed", "vh_dist_timeouts", "vh_dist_destroy",
 ]
 
 _lib = None
@@ -204,6 +205,7 @@ def load_library() -> C.CDLL:
     lib.vh_dist_connect.argtypes = [P, P]
     lib.vh_dist_broadcast_frame.argtypes = [P, P, P, P, P]
     lib.vh_dist_frame_consumed.argtypes = [P, P]
+    lib.vh_dist_timeouts.argtypes = [P]
     lib.vh_dist_destroy.argtypes = [P]
     lib.vh_dist_destroy.restype = None
     lib.vh_pipeline_push_host.argtypes = [P, P, P, P]
