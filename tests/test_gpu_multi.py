@@ -58,10 +58,13 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_partitioned_fused_equals_single(built_library, tmp_path, world):
+@pytest.mark.parametrize("world,transport", [(2, "nccl"), (2, "ipc"), (4, "nccl"), (8, "nccl")])
+def test_partitioned_fused_equals_single(built_library, tmp_path, world, transport, monkeypatch):
+    """transport: how the Python tracker moves frames and ICP sums -- "nccl" = symmetric-memory mailboxes + NCCL frame
+    broadcast (its default), "ipc" = the library's own vh_dist transport (CUDA IPC regions, what a C++ host uses)."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("VH_DIST_TRANSPORT", transport)
     import torch.multiprocessing as mp
 
     from voxelhashing_demo_b200 import Context

@@ -84,7 +84,15 @@ class PartitionedTracker:
         self._frame_ptrs = (0, 0)                            # device addresses of the (previous, latest) frame as this rank holds them
         self._dist = None                                   # vh_dist handle (C ABI transport: CUDA IPC, no NCCL on the data path)
         if world > 1:
-            self._setup_ipc_transport()
+            import os
+
+            # Frame transport of this Python tracker.  Default "nccl": symmetric-memory mailboxes + NCCL frame broadcast on
+            # its own stream (the broadcast of frame k+1 is issued as soon as its landing buffer is free, so the frame is
+            # pre-processed DURING Align(k)).  "ipc": the library's own transport (vh_dist_*, what a C++ host uses) -- the
+            # same results, but its push is ordered behind the pose of the previous frame and arrives when the persistent
+            # integrate grid already holds the SMs: 8 GPUs 2 071 vs 3 015 frames/s (r2).
+            if os.environ.get("VH_DIST_TRANSPORT", "nccl") == "ipc":
+                self._setup_ipc_transport()
             if self._dist is None:
                 self._setup_peer_exchange()
         # With the exchange fused into the ICP kernel the whole frame is stream-ordered device work, so it goes through
@@ -253,8 +261,9 @@ class PartitionedTracker:
             src = None
             if self.rank == 0:
                 src = d_depth.data_ptr()
-                if d_depth.is_cuda:
-                    d_depth.record_stream(main)
+            # The push is ordered behind this stream (which is ordered behind the pose of the previous frame).  Letting it run
+            # ahead (input_ready) was tried and withdrawn: with the landing-slot flow control spinning inside resident kernels a
+            # 4-GPU run with the default scheduling stopped making progress (r2), so the verified ordering stays.
             L_check = self.ctx.lib.vh_dist_broadcast_frame(self._dist, src, C.byref(frame), C.byref(ready), main.cuda_stream)
             if L_check != 0:
                 raise RuntimeError("vh_dist_broadcast_frame failed")
