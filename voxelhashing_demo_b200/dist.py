@@ -110,14 +110,14 @@ class PartitionedTracker:
     def _auto_tuning(cfg, world: int):
         """The Align grid (one 512-thread CTA per SM, the whole register file of each) and the persistent integrate grid
         cannot share an SM.  With a few image rows per rank the Align is a chain of exchange latencies, not work: a SMALL
-        grid (~6 pixels per thread) on its own SMs costs it little and lets tracking(k+1) run beside fusion(k) instead of
-        after it.  Measured on C4 at 2 mm (r2): 8 GPUs, 36 Align CTAs + 36 reserved SMs: 3 015 frames/s against 2 319 with the
-        default grid (Align 161 -> 199 us, integrate 205 -> 235 us, but side by side).  At 2-4 GPUs the fusion is several
-        times longer than the Align and giving up a quarter of the SMs costs more than the overlap returns."""
-        if world < 8:
+        grid on its own SMs costs it little and lets tracking(k+1) run beside fusion(k) instead of after it.  Measured on C4
+        at 2 mm (r2, frames/s, default grid -> split): 4 GPUs 1 430 -> 1 740 (40 CTAs + 40 reserved SMs), 8 GPUs 2 319 ->
+        3 058 (38 + 38; Align 161 -> 236 us, integrate 205 -> 231 us, but side by side).  With 2 ranks the fusion is five times
+        longer than the Align and giving up a quarter of the SMs costs more than the overlap returns."""
+        if world < 4:
             return None
         rows = (cfg.height + world - 1) // world
-        ctas = max(16, min(64, (rows * cfg.width + 3071) // 3072))
+        ctas = max(16, min(40, (rows * cfg.width + 3071) // 3072))
         return ctas, ctas
 
     def _setup_ipc_transport(self):
