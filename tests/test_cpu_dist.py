@@ -187,3 +187,43 @@ def test_streaming_respects_the_partition(tmp_path, oracle):
         # offered everyone's records, each rank takes back exactly what it streamed out and ends where it started
         assert int(r["moved"]) > 0 and int(r["offered"]) > int(r["moved"])
         assert int(r["accepted"]) == int(r["moved"]) and int(r["same"]) == 1
+
+
+def test_auto_tuning_splits_the_sms_only_when_the_align_is_latency_bound():
+    """PartitionedTracker._auto_tuning: the SM split between the Align grid and the integrate grid (measured on C4 at 2 mm:
+    a gain at 4 and 8 ranks, a loss at 2)."""
+    from voxelhashing_demo_b200.dist import PartitionedTracker
+
+    class Cfg:
+        width, height = 1280, 720
+
+    assert PartitionedTracker._auto_tuning(Cfg, 1) is None and PartitionedTracker._auto_tuning(Cfg, 2) is None
+    for world in (4, 8):
+        ctas, reserved = PartitionedTracker._auto_tuning(Cfg, world)
+        assert ctas == reserved and 16 <= ctas <= 40
+
+
+def test_bench_arms_describe_the_same_config():
+    """The own arm and the reference arm of bench.py must print the identical `config` object (the driver compares them)."""
+    import importlib.util
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("bench_for_test", root / "bench.py")
+    saved_fd1 = os.dup(1)                                   # bench.py points fd 1 at stderr on import: undo it afterwards
+    try:
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+    finally:
+        os.dup2(saved_fd1, 1)
+        os.close(saved_fd1)
+    from voxelhashing_demo_b200 import POLICY_REF_EXACT
+
+    cfg_own, _, _, _ = bench.workload_config("C2")
+    cfg_ref, _, _, _ = bench.workload_config("C2", policy=POLICY_REF_EXACT)
+    assert bench.config_dict("C2", cfg_own, 25) == bench.config_dict("C2", cfg_ref, 25)
+    c4 = bench.workload_config("C4", 8, 3)[0]
+    assert c4.voxelSize == 0.002 and c4.numVoxelBlocks == 1048576 and c4.numBuckets == 4000037 and (c4.width, c4.height) == (1280, 720)
+    assert "2 mm" in bench.config_dict("C4", c4, 25)["workload"]
+    sys.modules.pop("bench_for_test", None)
