@@ -56,7 +56,7 @@ struct vh_pipeline {
     bool overlap;
     bool fusedPre;                 // VH_PIPE_FUSED_PRE=1: pre-processing inside the Align kernel (see pushFrame)
     cudaStream_t fuseStream, trackStream, prepStream;
-    cudaEvent_t evIn, evPreR[kMapSets], evAlignedR[kMapSets];
+    cudaEvent_t evIn, evPreR[kMapSets], evAlignedR[kMapSets], evFrameSetR[kMapSets];
     cudaEvent_t evFused[kMapSets];
     bool fusePending;              // a fusion has been enqueued since the last reset
     int lastFusePar;
@@ -187,6 +187,7 @@ int vh_pipeline_create(vh_context* ctx, int icpIterations, int mode, int useGrap
         for (int i = 0; i < kMapSets; ++i) {
             chk(cudaEventCreateWithFlags(&p->evPreR[i], cudaEventDisableTiming));
             chk(cudaEventCreateWithFlags(&p->evAlignedR[i], cudaEventDisableTiming));
+            chk(cudaEventCreateWithFlags(&p->evFrameSetR[i], cudaEventDisableTiming));
         }
         chk(cudaStreamCreateWithPriority(&p->fuseStream, cudaStreamNonBlocking, least));
         for (int i = 0; i < kMapSets; ++i) chk(cudaEventCreateWithFlags(&p->evFused[i], cudaEventDisableTiming));
@@ -222,6 +223,7 @@ void vh_pipeline_destroy(vh_pipeline* p) {
     for (int i = 0; i < kMapSets; ++i) {
         if (p->evPreR[i]) cudaEventDestroy(p->evPreR[i]);
         if (p->evAlignedR[i]) cudaEventDestroy(p->evAlignedR[i]);
+        if (p->evFrameSetR[i]) cudaEventDestroy(p->evFrameSetR[i]);
     }
     for (int i = 0; i < kMapSets; ++i) if (p->evFused[i]) cudaEventDestroy(p->evFused[i]);
     cudaFree(p->modelVerts); cudaFree(p->modelNormals); cudaFree(p->d_poseBuf[0]);
@@ -285,6 +287,9 @@ static int pushFrameOverlap(vh_pipeline* p, const uint16_t* d_depth, cudaStream_
             PCUDA(cudaStreamWaitEvent(p->trackStream, p->evPreR[m], 0));
         }
         float* next = p->d_poseBuf[p->poseIdx ^ 1];
+        // `next` still holds the pose of frame k-2: the frame-constants kernel of that frame (fusion stream) must have read it
+        // (it runs two Aligns earlier in practice; the event makes it a guarantee)
+        if (p->frame >= 2) PCUDA(cudaStreamWaitEvent(p->trackStream, p->evFrameSetR[(m + 1) % kMapSets], 0));
         // [Application.cpp:73] + CameraTracking.cpp:35-67 + the pose chain, one launch
         PCUDA(enqueueIcp(p, m, fusedPre ? d_depth : nullptr, p->d_pose, next, p->trackStream, &nIcp));
         p->poseIdx ^= 1;
@@ -297,6 +302,7 @@ static int pushFrameOverlap(vh_pipeline* p, const uint16_t* d_depth, cudaStream_
     PCUDA(cudaStreamWaitEvent(st, p->evAlignedR[m], 0));                   // the caller's stream is ordered behind the pose
     PCUDA(cudaStreamWaitEvent(p->fuseStream, p->evAlignedR[m], 0));
     PCUDA(launch_set_frame_device(c, p->d_pose, nullptr, nullptr, p->fuseStream));   // SDF_Hashtable.cpp:15-21
+    PCUDA(cudaEventRecord(p->evFrameSetR[m], p->fuseStream));
     if (!p->haveFuseGraph[m]) {
         PCUDA(cudaStreamBeginCapture(p->fuseStream, cudaStreamCaptureModeThreadLocal));
         cudaError_t e = enqueueFusion(p, m, p->fuseStream, &nFuse);
