@@ -172,12 +172,12 @@ int vh_dist_connect(vh_dist* d, const void* handles) {
 int vh_dist_broadcast_frame(vh_dist* d, const uint16_t* d_depth, const uint16_t** d_frame, void** ready_event, vh_stream s) {
     if (!d || !d_frame || !ready_event || (d->rank == 0 && !d_depth)) return dfail(VH_ERR_INVALID, "vh_dist_broadcast_frame: bad argument");
     if (!d->connected) return dfail(VH_ERR_INVALID, "vh_dist_broadcast_frame: vh_dist_connect first");
+    if ((d->frameBytes & 15) != 0) return dfail(VH_ERR_INVALID, "vh_dist_broadcast_frame: W*H must be a multiple of 8");
     const int slot = (int)(d->pushed % kSlots);
     const unsigned long long seq = d->pushed + 1;
     if (d->rank == 0) {
         DCUDA(cudaEventRecord(d->evIn, reinterpret_cast<cudaStream_t>(s)));
         DCUDA(cudaStreamWaitEvent(d->stream, d->evIn, 0));
-        if ((d->frameBytes & 15) != 0) return dfail(VH_ERR_INVALID, "vh_dist_broadcast_frame: W*H must be a multiple of 8");
         k_frame_push<<<16, 256, 0, d->stream>>>(d->peers, d->world, reinterpret_cast<const uint4*>(d_depth), d->frameBytes / 16,
                                                 d->landingStride, slot, seq, d->ticket);
         DCUDA(cudaGetLastError());
@@ -195,9 +195,9 @@ int vh_dist_broadcast_frame(vh_dist* d, const uint16_t* d_depth, const uint16_t*
 int vh_dist_frame_consumed(vh_dist* d, vh_stream s) {
     if (!d) return dfail(VH_ERR_INVALID, "vh_dist_frame_consumed: null argument");
     if (d->consumed >= d->pushed) return dfail(VH_ERR_INVALID, "vh_dist_frame_consumed: no frame outstanding");
-    d->consumed += 1;
-    k_frame_consumed<<<1, 32, 0, reinterpret_cast<cudaStream_t>(s)>>>(d->peers.r[0], d->rank, d->consumed);
+    k_frame_consumed<<<1, 32, 0, reinterpret_cast<cudaStream_t>(s)>>>(d->peers.r[0], d->rank, d->consumed + 1);
     DCUDA(cudaGetLastError());
+    d->consumed += 1;
     return VH_OK;
 }
 
