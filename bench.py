@@ -738,6 +738,10 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict("C2", cfg, n_unique),
             "policy": "the reference's as-built arithmetic (it has no other); its kernels take the table geometry, voxel size and truncation of the config"}
+    if args.gpus > 1:
+        base["note_multi_gpu"] = ("the reference is a one-GPU program with the image size baked in at 640x480 (SURVEY quirk Q15): it cannot run config C4 "
+                                  "(1280x720, partitioned over GPUs), which is what the own arm runs at --gpus > 1.  This line is its C2 number on ONE GPU; "
+                                  "dividing a C4 value at N GPUs by it compares different workloads")
     try:
         import torch
 
